@@ -1,0 +1,110 @@
+/* musicgan_b200 -- C ABI of the B200 (sm_100a) hot path of Ipsedo/MusicGAN.
+ *
+ * The reference has no FFI of its own (it is pure Python on torch): the boundary a maintainer
+ * binds is this header, called from `music_gan/audio/functions.py` and `music_gan/networks/*.py`
+ * through ctypes (INTEGRATION.md shows the stub).  Every entry point names the reference
+ * function (file:line under /root/reference/music_gan/) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - every call only enqueues work on `stream` (a cudaStream_t) and never synchronises;
+ *   - the caller owns every buffer; scratch is passed in (`ws`) and sized by *_workspace_bytes;
+ *   - return value: 0 = MG_OK, negative = mgError (see mg_error_string); no exceptions, no
+ *     hidden allocation, no CPU fallback.
+ */
+#ifndef MUSICGAN_B200_H
+#define MUSICGAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mgStream; /* cudaStream_t */
+
+enum mgError {
+    MG_OK = 0,
+    MG_ERR_BAD_ARG = -1,       /* null pointer, non-positive size, misaligned buffer        */
+    MG_ERR_UNSUPPORTED = -2,   /* shape / parameter outside what the sm_100a kernels cover  */
+    MG_ERR_WORKSPACE = -3,     /* workspace smaller than *_workspace_bytes                  */
+    MG_ERR_LAUNCH = -4,        /* CUDA launch / runtime error (cudaGetLastError text logged) */
+    MG_ERR_NO_DEVICE = -5      /* no sm_100 device visible                                  */
+};
+
+int mg_version(void);
+const char* mg_error_string(int err);
+/* last CUDA error text recorded by a failing call of this thread ("" if none) */
+const char* mg_last_cuda_error(void);
+int mg_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Audio transform constants: audio/constant.py:1-4
+ * ---------------------------------------------------------------------------------------- */
+#define MG_N_FFT 1024
+#define MG_N_VEC 512
+#define MG_STFT_STRIDE 256
+#define MG_SAMPLE_RATE 44100
+
+/* Integer frame / chunk plan of audio/functions.py:53-62 (T = 1 + N / hop) and :76-92
+ * (T-1 difference columns, leading (T-1) % nb_vec dropped, rest split in nb_vec-wide chunks).
+ * Host-only arithmetic; bit exact by construction. */
+int mg_chunk_plan(int64_t n_samples, int hop, int nb_vec, int64_t* n_frames, int64_t* head, int64_t* n_chunks);
+
+/* Host helpers that fill the two constant vectors the kernels take as arguments, computed in
+ * double precision: periodic Hann window (functions.py:51) and the normalised Bark gain
+ * 6*asinh(linspace(20,22050,F)/600)/||.||2 (functions.py:29-33).  The Python binding passes
+ * torch's own vectors instead so that they are bit-identical to the reference's. */
+void mg_fill_hann_host(float* window_host, int n_fft);
+void mg_fill_bark_gain_host(float* gain_host, int n_bins);
+
+/* ------------------------------------------------------------------------------------------
+ * Forward transform  (wav -> STFT -> magnitude / instantaneous frequency chunks)
+ *   replaces audio/functions.py:38-62 wav_to_stft (minus the file read) and
+ *            audio/functions.py:65-94 stft_to_phase_magn (incl. :13-35 diff/unwrap/bark)
+ *
+ * wav        [batch][channels][n_samples] fp32, clip stride `clip_stride` elements (mono mean over
+ *            channels as functions.py:49); n_fft = 1024, hop = 256, nb_vec = 512 only.
+ * window     [1024] fp32 analysis window, bark_gain [512] fp32.
+ * magn/ifreq [batch][n_chunks][512][512] fp32, time fastest, normalised to [-1, 1] per clip.
+ * minmax     [batch][4] fp32: raw magn min, magn max, IF min, IF max of each clip (functions.py:79-82).
+ * ---------------------------------------------------------------------------------------- */
+size_t mg_stft_magif_workspace_bytes(int64_t n_samples, int batch);
+int mg_stft_magif_f32(const float* wav, int64_t n_samples, int channels, int64_t clip_stride, int batch,
+                      const float* window, const float* bark_gain,
+                      float* magn, float* ifreq, float* minmax,
+                      void* ws, size_t ws_bytes, mgStream stream);
+
+/* STFT only: functions.py:38-62.  out [batch][T][512] complex64 (re,im interleaved), FRAME major
+ * (the reference's (512, T) tensor is the transposed view of this memory, stride (1, 512)). */
+int mg_stft_c64(const float* wav, int64_t n_samples, int channels, int64_t clip_stride, int batch,
+                const float* window, float* out_c64, mgStream stream);
+
+/* Post-FFT stage on a caller supplied complex STFT: functions.py:65-94.
+ * stft: complex64 element (f, t) of clip b at stft[2*(b*batch_stride + f*stride_f + t*stride_t)].
+ * Used for the staged parity protocol and by stft_to_phase_magn(). */
+size_t mg_phase_magn_workspace_bytes(int64_t n_frames, int batch);
+int mg_phase_magn_from_stft(const float* stft_c64, int64_t n_frames, int64_t stride_f, int64_t stride_t,
+                            int64_t batch_stride, int batch, const float* bark_gain,
+                            float* magn, float* ifreq, float* minmax,
+                            void* ws, size_t ws_bytes, mgStream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Inverse transform (magnitude / IF images -> cumulative phase -> complex spectrum -> iSTFT)
+ *   replaces audio/functions.py:97-137 magn_phase_to_wav (minus the file write :139)
+ *
+ * magn_phase [n_clips][imgs_per_clip][2][512][W] fp32; the images of a clip are concatenated
+ *            along time (functions.py:108-109), each clip is de-normalised on its own
+ *            (generate.py:61-65 passes one image per call).
+ * wav        [n_clips][256 * (imgs_per_clip*W - 1)] fp32.
+ * ---------------------------------------------------------------------------------------- */
+size_t mg_istft_workspace_bytes(int n_clips, int imgs_per_clip, int width);
+int mg_istft_from_magif_f32(const float* magn_phase, int n_clips, int imgs_per_clip, int width,
+                            const float* window, const float* bark_gain,
+                            float* wav, void* ws, size_t ws_bytes, mgStream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUSICGAN_B200_H */

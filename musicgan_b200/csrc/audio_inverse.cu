@@ -1,0 +1,263 @@
+// Inverse spectrogram transform for sm_100a: (magnitude, instantaneous-frequency) images ->
+// cumulative phase -> complex spectrum -> iSTFT (Hann 1024 / hop 256, centred) -> waveform.
+//
+// Replaces reference music_gan/audio/functions.py:97-137 (magn_phase_to_wav without the file write).
+//
+//   k_inv_magn_minmax  (m+1)/2 / bark  -> per-clip min / max                      (:111-113)
+//   k_inv_phase_scan   phase affine map, STRICTLY SEQUENTIAL float32 running sum along time per bin
+//                      (:115-118; SURVEY B.3: a parallel or fp64 scan only reaches 44 dB on coherent
+//                      phase), % 2pi, magn * (cos, sin) -> X[t][f] frame major      (:120-123)
+//   k_istft            per frame: half-complex -> packed 512-pt spectrum, inverse FFT (fft512.cuh),
+//                      Hann, overlap-add of 4 frames in registers (ascending frame order), divide by the
+//                      window envelope, trim n_fft/2 at both ends                    (:125-137)
+#include "common.cuh"
+#include "fft512.cuh"
+#include "fft_tables.h"
+#include "tables.cuh"
+
+namespace mg {
+
+constexpr int kIBins = 512;
+constexpr int kIHop = 256;
+constexpr int kINfft = 1024;
+
+__device__ __forceinline__ int64_t img_index(int clip, int imgs, int W, int ch, int f, int64_t tt) {
+    const int i = (int)(tt / W), w = (int)(tt % W);
+    return ((((int64_t)clip * imgs + i) * 2 + ch) * kIBins + f) * (int64_t)W + w;
+}
+
+// functions.py:111-112
+__device__ __forceinline__ float magn_unscaled(float m, float gain) {
+    return __fdiv_rn(__fdiv_rn(__fadd_rn(m, 1.0f), 2.0f), gain);
+}
+
+// grid (blocks, n_clips), block 256
+__global__ void __launch_bounds__(256)
+k_inv_magn_minmax(const float* __restrict__ mp, int imgs, int W, const float* __restrict__ bark, int* __restrict__ keys) {
+    __shared__ float redf[2][8];
+    const int clip = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float mn = INFINITY, mx = -INFINITY;
+    const int64_t per_img = (int64_t)kIBins * W;
+    for (int i = 0; i < imgs; ++i) {
+        const float* base = mp + (((int64_t)clip * imgs + i) * 2 + 0) * per_img;
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + tid; e < per_img; e += (int64_t)gridDim.x * blockDim.x) {
+            const int f = (int)(e / W);
+            const float v = magn_unscaled(base[e], bark[f]);
+            mn = fminf(mn, v); mx = fmaxf(mx, v);
+        }
+    }
+    mn = warp_min(mn); mx = warp_max(mx);
+    if (lane == 0) { redf[0][warp] = mn; redf[1][warp] = mx; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w) { mn = fminf(mn, redf[0][w]); mx = fmaxf(mx, redf[1][w]); }
+        if (mn <= mx) {
+            atomicMin(&keys[clip * 4 + 0], float_key(mn));
+            atomicMax(&keys[clip * 4 + 1], float_key(mx));
+        }
+    }
+}
+
+// grid (4, n_clips), block 128: one warp = 32 bins x the whole time axis of one clip
+__global__ void __launch_bounds__(128)
+k_inv_phase_scan(const float* __restrict__ mp, int imgs, int W, const float* __restrict__ bark,
+                 const int* __restrict__ keys, float2* __restrict__ X) {
+    __shared__ float tp[4][32][33];
+    __shared__ float tm[4][32][33];
+    const int clip = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f0 = (blockIdx.x * 4 + warp) * 32;
+    const int64_t Wt = (int64_t)imgs * W;
+    const float range = __fsub_rn(key_float(keys[clip * 4 + 1]), key_float(keys[clip * 4 + 0]));   // :113
+    const float gain = bark[f0 + lane];
+    float acc = 0.0f;
+    for (int64_t tt0 = 0; tt0 < Wt; tt0 += 32) {
+        const int64_t tt = tt0 + lane;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            float p = 0.0f, m = 0.0f;
+            if (tt < Wt) {
+                p = __ldcs(mp + img_index(clip, imgs, W, 1, f0 + r, tt));
+                m = __ldcs(mp + img_index(clip, imgs, W, 0, f0 + r, tt));
+            }
+            tp[warp][r][lane] = p; tm[warp][r][lane] = m;
+        }
+        __syncwarp();
+        const int n = (int)min((int64_t)32, Wt - tt0);
+        for (int j = 0; j < n; ++j) {
+            // :115  (phase + 1.) / 2. * 2. * pi - pi, every op rounded to float32
+            float p = tp[warp][lane][j];
+            p = __fsub_rn(__fmul_rn(__fmul_rn(__fdiv_rn(__fadd_rn(p, 1.0f), 2.0f), 2.0f), kPiF), kPiF);
+            acc = (tt0 + j == 0) ? p : __fadd_rn(acc, p);                  // :117-118 sequential fp32 sum
+            const float ph = remainder_pos(acc, kTwoPiF);                   // :120
+            float sn, cs;
+            sincosf(ph, &sn, &cs);
+            const float m = __fdiv_rn(magn_unscaled(tm[warp][lane][j], gain), range);
+            X[((int64_t)clip * Wt + tt0 + j) * kIBins + f0 + lane] = make_float2(__fmul_rn(m, cs), __fmul_rn(m, sn));
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int kIstftWarps = 8;
+constexpr int kHopsPerWarp = 16;
+
+struct IstftSmem {
+    float2 win2[512];        // (w[2n], w[2n+1]) * sqrt(sum w^2) / 1024
+    float wsq[kINfft];       // w^2 (envelope terms)
+    FftTables fft;
+    float2 w1024[512];
+    float2 ex[kIstftWarps][512];
+    double red[kIstftWarps];
+};
+
+// grid (ceil(n_hops / (8*16)), n_clips), block 256
+__global__ void __launch_bounds__(kIstftWarps * 32, 2)
+k_istft(const float2* __restrict__ X, int64_t Wt, const float* __restrict__ window,
+        const DeviceTables* __restrict__ tables, float* __restrict__ wav) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    IstftSmem& s = *reinterpret_cast<IstftSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int clip = blockIdx.y;
+    const int64_t n_hops = Wt - 1;
+
+    double part = 0.0;
+    for (int i = tid; i < kINfft; i += blockDim.x) { const double w = window[i]; part += w * w; s.wsq[i] = __fmul_rn(window[i], window[i]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s.red[warp] = part;
+    {
+        const float2* src = reinterpret_cast<const float2*>(&tables->fft);
+        float2* dst = reinterpret_cast<float2*>(&s.fft);
+        for (int i = tid; i < (int)(sizeof(FftTables) / sizeof(float2)); i += blockDim.x) dst[i] = src[i];
+        for (int i = tid; i < 512; i += blockDim.x) s.w1024[i] = tables->w1024[i];
+    }
+    __syncthreads();
+    {
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < kIstftWarps; ++w) tot += s.red[w];
+        // * sqrt(sum w^2): inverse_spectrogram(normalized=True); / 1024: irfft norm (the merge keeps a factor 2
+        // and the forward-FFT-with-conjugates trick a factor 512)
+        const float scale = (float)(sqrt(tot) / 1024.0);
+        for (int i = tid; i < 512; i += blockDim.x)
+            s.win2[i] = make_float2(window[2 * i] * scale, window[2 * i + 1] * scale);
+    }
+    __syncthreads();
+
+    const int64_t h0 = ((int64_t)blockIdx.x * kIstftWarps + warp) * kHopsPerWarp;
+    if (h0 >= n_hops) return;
+    const int64_t h1 = min(n_hops, h0 + kHopsPerWarp);
+    float2* ex = s.ex[warp];
+    const float2* Xc = X + (int64_t)clip * Wt * kIBins;
+    float* out = wav + (int64_t)clip * n_hops * kIHop;
+
+    float2 acc[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) acc[m] = make_float2(0.f, 0.f);
+
+    for (int64_t t = h0 - 1; t <= h1 + 1; ++t) {
+        // slide the 1024-sample accumulation window forward by one hop (= 4 slots of 64 samples)
+#pragma unroll
+        for (int m = 0; m < 12; ++m) acc[m] = acc[m + 4];
+#pragma unroll
+        for (int m = 12; m < 16; ++m) acc[m] = make_float2(0.f, 0.f);
+
+        if (t >= 0 && t < Wt) {
+            const float2* row = Xc + t * kIBins;
+            float2 v[16];
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const int k = lane + 32 * m;
+                float2 xk = row[k];
+                float2 xp = (k == 0) ? make_float2(0.f, 0.f) : row[kIBins - k];   // Nyquist row is zero (:125-126)
+                if (k == 0) xk.y = 0.f;                                          // C2R ignores Im X[0]
+                const float2 z = irfft_merge(xk, xp, s.w1024[k]);
+                v[fft_slot(m)] = make_float2(z.x, -z.y);                         // conj: inverse via forward FFT
+            }
+            fft512_pass1_store(v, ex, lane);
+            __syncwarp();
+            fft512_pass2_load(v, ex, lane);
+            __syncwarp();
+            fft512_pass2_store(v, ex, s.fft, lane);
+            __syncwarp();
+            fft512_pass3_load(v, ex, lane);
+            __syncwarp();
+            fft512_pass3_finish(v, s.fft, lane);
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const float2 z = v[fft_slot(m)];
+                const float2 w = s.win2[lane + 32 * m];
+                // x[2n] = Re, x[2n+1] = -Im (conj back); frames are added in ascending t
+                acc[m].x = __fadd_rn(acc[m].x, z.x * w.x);
+                acc[m].y = __fadd_rn(acc[m].y, -z.y * w.y);
+            }
+        }
+        const int64_t h = t - 2;
+        if (h >= h0 && h < h1) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int q0 = 2 * lane + 64 * m;
+                float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+                for (int i = 3; i >= 0; --i) {           // ascending frame index t' = h + 2 - i
+                    const int64_t tf = h + 2 - i;
+                    if (tf >= 0 && tf < Wt) { e0 = __fadd_rn(e0, s.wsq[q0 + 256 * i]); e1 = __fadd_rn(e1, s.wsq[q0 + 1 + 256 * i]); }
+                }
+                float2 o = make_float2(__fdiv_rn(acc[m].x, e0), __fdiv_rn(acc[m].y, e1));
+                __stcs(reinterpret_cast<float2*>(out + h * kIHop + q0), o);
+            }
+        }
+    }
+}
+
+struct InverseWs { float2* X; int* keys; size_t bytes; };
+static InverseWs carve_inverse_ws(void* ws, int n_clips, int64_t Wt) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_x = take((size_t)n_clips * Wt * kIBins * sizeof(float2));
+    const size_t o_k = take((size_t)n_clips * 4 * sizeof(int));
+    InverseWs w; char* b = (char*)ws;
+    w.X = (float2*)(b + o_x); w.keys = (int*)(b + o_k); w.bytes = off;
+    return w;
+}
+
+}  // namespace mg
+
+using namespace mg;
+
+extern "C" {
+
+size_t mg_istft_workspace_bytes(int n_clips, int imgs_per_clip, int width) {
+    if (n_clips <= 0 || imgs_per_clip <= 0 || width <= 0) return 0;
+    return carve_inverse_ws(nullptr, n_clips, (int64_t)imgs_per_clip * width).bytes;
+}
+
+int mg_istft_from_magif_f32(const float* magn_phase, int n_clips, int imgs_per_clip, int width,
+                            const float* window, const float* bark_gain,
+                            float* wav, void* ws, size_t ws_bytes, mgStream stream) {
+    if (!magn_phase || !window || !bark_gain || !wav || !ws) return MG_ERR_BAD_ARG;
+    if (n_clips <= 0 || imgs_per_clip <= 0 || width <= 0) return MG_ERR_BAD_ARG;
+    const int64_t Wt = (int64_t)imgs_per_clip * width;
+    if (Wt < 2) return MG_ERR_UNSUPPORTED;
+    if (n_clips > 65535) return MG_ERR_UNSUPPORTED;
+    if (((uintptr_t)ws & 255) != 0 || ((uintptr_t)wav & 7) != 0) return MG_ERR_BAD_ARG;
+    InverseWs w = carve_inverse_ws(ws, n_clips, Wt);
+    if (ws_bytes < w.bytes) return MG_ERR_WORKSPACE;
+    cudaError_t e = ensure_tables();
+    if (e != cudaSuccess) { set_last_cuda_error("tables", e); return MG_ERR_LAUNCH; }
+    cudaStream_t st = (cudaStream_t)stream;
+    launch_init_keys(w.keys, n_clips, st);
+    const int64_t per_img = (int64_t)kIBins * width;
+    const unsigned gx = (unsigned)max((int64_t)1, min((int64_t)592, per_img / 1024));
+    k_inv_magn_minmax<<<dim3(gx, n_clips), 256, 0, st>>>(magn_phase, imgs_per_clip, width, bark_gain, w.keys);
+    k_inv_phase_scan<<<dim3(4, n_clips), 128, 0, st>>>(magn_phase, imgs_per_clip, width, bark_gain, w.keys, w.X);
+    const int64_t n_hops = Wt - 1;
+    const unsigned gh = (unsigned)((n_hops + kIstftWarps * kHopsPerWarp - 1) / (kIstftWarps * kHopsPerWarp));
+    static bool attr_done = false;
+    if (!attr_done) { cudaFuncSetAttribute(k_istft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IstftSmem)); attr_done = true; }
+    k_istft<<<dim3(gh, n_clips), kIstftWarps * 32, sizeof(IstftSmem), st>>>(w.X, Wt, window, device_tables_ptr(), wav);
+    return check_launch("istft");
+}
+
+}  // extern "C"
