@@ -39,6 +39,14 @@ const char* mg_error_string(int err);
 const char* mg_last_cuda_error(void);
 int mg_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Optional per-kernel timing (CUDA events recorded on the caller's stream around every kernel the
+ * library launches).  Off by default; bench.py switches it on for the timed region to report the
+ * dominant kernel's duration.  mg_profile_collect synchronises the recorded events, returns the
+ * number of distinct kernels (<= max_entries) and fills name / total milliseconds / launch count,
+ * then clears the record. */
+void mg_profile_enable(int on);
+int mg_profile_collect(int max_entries, const char** names, float* total_ms, int* launches);
+
 /* ------------------------------------------------------------------------------------------
  * Audio transform constants: audio/constant.py:1-4
  * ---------------------------------------------------------------------------------------- */
@@ -103,6 +111,15 @@ size_t mg_istft_workspace_bytes(int n_clips, int imgs_per_clip, int width);
 int mg_istft_from_magif_f32(const float* magn_phase, int n_clips, int imgs_per_clip, int width,
                             const float* window, const float* bark_gain,
                             float* wav, void* ws, size_t ws_bytes, mgStream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Test-only probe of the tcgen05 / TMEM conventions the convolution kernels rely on (one tile).
+ * mode 0: A [Ra][K], B [N][K] bf16 (K contiguous);  D[m][n] = sum_k A[row_off + (m/8)*grp_rows + m%8][k] * B[n][k]
+ * mode 1: A [K][128], B [K][N] bf16 (M / N contiguous);  D[m][n] = sum_k A[k][m] * B[k][n]
+ * D [128][N] fp32.
+ * ---------------------------------------------------------------------------------------- */
+int mg_debug_umma_gemm(const void* A, const void* B, float* D, int K, int N, int mode, int Ra, int row_off,
+                       int grp_rows, mgStream stream);
 
 #ifdef __cplusplus
 }

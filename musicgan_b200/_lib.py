@@ -52,6 +52,9 @@ def _declare(l: ctypes.CDLL) -> None:
     l.mg_phase_magn_workspace_bytes.argtypes = [c_int64, c_int]
     l.mg_phase_magn_from_stft.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    l.mg_profile_enable.argtypes = [c_int]
+    l.mg_profile_enable.restype = None
+    l.mg_profile_collect.argtypes = [c_int, POINTER(c_char_p), POINTER(c_float), POINTER(c_int)]
     if hasattr(l, "mg_istft_workspace_bytes"):
         l.mg_istft_workspace_bytes.restype = c_size_t
         l.mg_istft_workspace_bytes.argtypes = [c_int, c_int, c_int]
@@ -72,3 +75,16 @@ def chunk_plan(n_samples: int, hop: int = 256, nb_vec: int = 512):
     t, h, c = c_int64(), c_int64(), c_int64()
     check(lib().mg_chunk_plan(n_samples, hop, nb_vec, ctypes.byref(t), ctypes.byref(h), ctypes.byref(c)), "mg_chunk_plan")
     return t.value, h.value, c.value
+
+
+def profile_enable(on: bool) -> None:
+    lib().mg_profile_enable(1 if on else 0)
+
+
+def profile_collect(max_entries: int = 64):
+    """{kernel name: (total ms, launches)} of the launches recorded since the last collect."""
+    names = (c_char_p * max_entries)()
+    ms = (c_float * max_entries)()
+    cnt = (c_int * max_entries)()
+    n = lib().mg_profile_collect(max_entries, names, ms, cnt)
+    return {names[i].decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}

@@ -399,10 +399,14 @@ static ForwardWs carve_forward_ws(void* ws, int64_t n_frames, int batch) {
 static int run_post_fft(const ForwardWs& w, int64_t n_frames, int batch, int64_t head, int64_t n_chunks,
                         float* magn, float* ifreq, float* minmax, cudaStream_t st) {
     const int n_seg = (int)((n_frames + kSeg - 1) / kSeg);
-    k_unwrap_aggregate<<<dim3(n_seg, batch), kBins, 0, st>>>(w.phi, n_frames, n_seg, w.agg, w.bnd);
-    k_unwrap_carry<<<batch, kBins, 0, st>>>(w.agg, n_seg);
-    k_ifreq<<<dim3(n_seg, batch), kBins, 0, st>>>(w.phi, n_frames, n_seg, w.agg, w.bnd, w.keys);
+    { ProfScope ps("k_unwrap_aggregate", st);
+      k_unwrap_aggregate<<<dim3(n_seg, batch), kBins, 0, st>>>(w.phi, n_frames, n_seg, w.agg, w.bnd); }
+    { ProfScope ps("k_unwrap_carry", st);
+      k_unwrap_carry<<<batch, kBins, 0, st>>>(w.agg, n_seg); }
+    { ProfScope ps("k_ifreq", st);
+      k_ifreq<<<dim3(n_seg, batch), kBins, 0, st>>>(w.phi, n_frames, n_seg, w.agg, w.bnd, w.keys); }
     if (n_chunks > 0) {
+        ProfScope ps("k_normalise_chunk", st);
         k_normalise_chunk<<<dim3((unsigned)(n_chunks * kBins / 32), kBins / 128, batch), 256, 0, st>>>(
             w.magn, w.phi, n_frames, head, n_chunks, w.keys, magn, ifreq, minmax);
     }
@@ -442,6 +446,7 @@ static int launch_stft(int mode, const float* wav, int64_t n_samples, int channe
     const int64_t n_frames = 1 + n_samples / kHop;
     const dim3 grid((unsigned)((n_frames + kFramesPerCta - 1) / kFramesPerCta), batch);
     const size_t smem = sizeof(StftSmem);
+    ProfScope ps("k_stft", st);
     if (mode == STFT_POLAR) {
         static bool attr_done = false;
         if (!attr_done) { cudaFuncSetAttribute(k_stft<STFT_POLAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
@@ -508,8 +513,9 @@ int mg_phase_magn_from_stft(const float* stft_c64, int64_t n_frames, int64_t str
     launch_init_keys(w.keys, batch, st);
     const int64_t total = n_frames * kBins;
     const unsigned gx = (unsigned)min((int64_t)4096, (total + 255) / 256);
-    k_polar_from_stft<<<dim3(gx, batch), 256, 0, st>>>(reinterpret_cast<const float2*>(stft_c64), n_frames, stride_f, stride_t,
-                                                       batch_stride, bark_gain, w.phi, w.magn, w.keys);
+    { ProfScope ps("k_polar_from_stft", st);
+      k_polar_from_stft<<<dim3(gx, batch), 256, 0, st>>>(reinterpret_cast<const float2*>(stft_c64), n_frames, stride_f, stride_t,
+                                                         batch_stride, bark_gain, w.phi, w.magn, w.keys); }
     int rc = check_launch("k_polar_from_stft");
     if (rc) return rc;
     return run_post_fft(w, n_frames, batch, head, n_chunks, magn, ifreq, minmax, st);

@@ -250,13 +250,16 @@ int mg_istft_from_magif_f32(const float* magn_phase, int n_clips, int imgs_per_c
     launch_init_keys(w.keys, n_clips, st);
     const int64_t per_img = (int64_t)kIBins * width;
     const unsigned gx = (unsigned)max((int64_t)1, min((int64_t)592, per_img / 1024));
-    k_inv_magn_minmax<<<dim3(gx, n_clips), 256, 0, st>>>(magn_phase, imgs_per_clip, width, bark_gain, w.keys);
-    k_inv_phase_scan<<<dim3(4, n_clips), 128, 0, st>>>(magn_phase, imgs_per_clip, width, bark_gain, w.keys, w.X);
+    { ProfScope ps("k_inv_magn_minmax", st);
+      k_inv_magn_minmax<<<dim3(gx, n_clips), 256, 0, st>>>(magn_phase, imgs_per_clip, width, bark_gain, w.keys); }
+    { ProfScope ps("k_inv_phase_scan", st);
+      k_inv_phase_scan<<<dim3(4, n_clips), 128, 0, st>>>(magn_phase, imgs_per_clip, width, bark_gain, w.keys, w.X); }
     const int64_t n_hops = Wt - 1;
     const unsigned gh = (unsigned)((n_hops + kIstftWarps * kHopsPerWarp - 1) / (kIstftWarps * kHopsPerWarp));
     static bool attr_done = false;
     if (!attr_done) { cudaFuncSetAttribute(k_istft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IstftSmem)); attr_done = true; }
-    k_istft<<<dim3(gh, n_clips), kIstftWarps * 32, sizeof(IstftSmem), st>>>(w.X, Wt, window, device_tables_ptr(), wav);
+    { ProfScope ps("k_istft", st);
+      k_istft<<<dim3(gh, n_clips), kIstftWarps * 32, sizeof(IstftSmem), st>>>(w.X, Wt, window, device_tables_ptr(), wav); }
     return check_launch("istft");
 }
 

@@ -20,6 +20,14 @@ inline int check_launch(const char* where) {
     return MG_OK;
 }
 
+// RAII stage timer (no-op unless mg_profile_enable(1)): records an event pair on `st`.
+struct ProfScope {
+    int slot;
+    cudaStream_t st;
+    ProfScope(const char* name, cudaStream_t st);
+    ~ProfScope();
+};
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Monotone int key of a float (for atomicMin / atomicMax on floats of either sign).

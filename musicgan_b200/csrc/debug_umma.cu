@@ -1,0 +1,84 @@
+// Probe / unit-test entry for the UMMA conventions in umma.cuh (descriptor bit layout, canonical
+// no-swizzle staging, row-offset starts, MN-major operands, TMEM lane mapping).  One CTA, one tile.
+// Not on any product path; called only by tests/test_umma_probe_gpu.py.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace mg {
+using namespace umma;
+
+// stage G[rows][cols] (cols contiguous, bf16) as S[(c * pitch + r)] = G[r][8c .. 8c+7]  (16-byte chunks)
+__device__ void stage_chunks(const __nv_bfloat16* __restrict__ g, int rows, int cols, uint4* s, int pitch) {
+    const int chunks = cols / 8;
+    for (int i = threadIdx.x; i < rows * chunks; i += blockDim.x) {
+        const int r = i / chunks, c = i % chunks;
+        s[c * pitch + r] = *reinterpret_cast<const uint4*>(g + (size_t)r * cols + 8 * c);
+    }
+}
+
+// mode 0: A [Ra][K] K-major rows, B [N][K] K-major rows.  D[m][n] = sum_k A[row_off + (m/8)*grp_rows + m%8][k] B[n][k]
+// mode 1: A [K][128] MN-major, B [K][N] MN-major.          D[m][n] = sum_k A[k][m] B[k][n]
+__global__ void __launch_bounds__(128)
+k_debug_umma(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, float* __restrict__ D,
+             int K, int N, int mode, int Ra, int row_off, int grp_rows) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint4* sA; uint4* sB; int pA, pB;
+    if (mode == 0) { pA = Ra + 1; pB = N + 1; } else { pA = K + 1; pB = K + 1; }
+    sA = reinterpret_cast<uint4*>(smem);
+    sB = sA + (mode == 0 ? (K / 8) * pA : (128 / 8) * pA);
+    if (mode == 0) { stage_chunks(A, Ra, K, sA, pA); stage_chunks(B, N, K, sB, pB); }
+    else           { stage_chunks(A, K, 128, sA, pA); stage_chunks(B, K, N, sB, pB); }
+    if (warp == 0) tmem_alloc(&tmem_base, 256);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = tmem_base;
+    if (tid == 0) {
+        const uint32_t idesc = instr_desc_bf16(N, mode == 1, mode == 1);
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+        for (int kk = 0; kk < K / 16; ++kk) {
+            uint64_t da, db;
+            if (mode == 0) {
+                da = smem_desc(a0 + (row_off + kk * 2 * pA) * 16, pA * 16, grp_rows * 16);
+                db = smem_desc(b0 + (kk * 2 * pB) * 16, pB * 16, 128);
+            } else {
+                da = smem_desc(a0 + (kk * 16) * 16, 128, pA * 16);
+                db = smem_desc(b0 + (kk * 16) * 16, 128, pB * 16);
+            }
+            mma_bf16(tm, da, db, idesc, kk > 0);
+        }
+        mma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    for (int n0 = 0; n0 < N; n0 += 16) {
+        float v[16];
+        tmem_ld16(tm + ((uint32_t)(warp * 32) << 16) + n0, v);
+        tmem_wait_ld();
+        const int m = warp * 32 + lane;
+        for (int j = 0; j < 16; ++j) D[(size_t)m * N + n0 + j] = v[j];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 256);
+}
+}  // namespace mg
+
+extern "C" int mg_debug_umma_gemm(const void* A, const void* B, float* D, int K, int N, int mode, int Ra, int row_off,
+                                  int grp_rows, mgStream stream) {
+    using namespace mg;
+    if (!A || !B || !D || K % 16 || N % 16 || N < 16 || N > 256) return MG_ERR_BAD_ARG;
+    size_t bytes;
+    if (mode == 0) bytes = ((size_t)(K / 8) * (Ra + 1) + (size_t)(K / 8) * (N + 1)) * 16;
+    else bytes = ((size_t)16 * (K + 1) + (size_t)(N / 8) * (K + 1)) * 16;
+    if (bytes > 200 * 1024) return MG_ERR_UNSUPPORTED;
+    cudaFuncSetAttribute(k_debug_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    k_debug_umma<<<1, 128, bytes, (cudaStream_t)stream>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, D, K, N, mode, Ra,
+                                                          row_off, grp_rows);
+    return check_launch("k_debug_umma");
+}

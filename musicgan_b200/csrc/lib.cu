@@ -10,9 +10,47 @@ static thread_local char g_last_error[256] = "";
 void set_last_cuda_error(const char* where, cudaError_t e) {
     snprintf(g_last_error, sizeof(g_last_error), "%s: %s", where, cudaGetErrorString(e));
 }
+
+// ---- stage profiler ----------------------------------------------------------------------------
+static bool g_prof_on = false;
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+static cudaEvent_t take_event() {
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+ProfScope::ProfScope(const char* name, cudaStream_t s) : slot(-1), st(s) {
+    if (!g_prof_on) return;
+    ProfRec r{name, take_event(), take_event()};
+    cudaEventRecord(r.a, st);
+    slot = (int)g_prof.size();
+    g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+    if (slot >= 0) cudaEventRecord(g_prof[slot].b, st);
+}
 }  // namespace mg
 
 extern "C" {
+
+void mg_profile_enable(int on) { mg::g_prof_on = on != 0; }
+
+int mg_profile_collect(int max_entries, const char** names, float* total_ms, int* launches) {
+    int n = 0;
+    for (auto& r : mg::g_prof) {
+        cudaEventSynchronize(r.b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        int k = 0;
+        for (; k < n; ++k) if (strcmp(names[k], r.name) == 0) break;
+        if (k == n) { if (n >= max_entries) continue; names[n] = r.name; total_ms[n] = 0.f; launches[n] = 0; ++n; }
+        total_ms[k] += ms; launches[k] += 1;
+        mg::g_event_pool.push_back(r.a); mg::g_event_pool.push_back(r.b);
+    }
+    mg::g_prof.clear();
+    return n;
+}
 
 int mg_version(void) { return 100; }   // 0.1.0
 
