@@ -113,6 +113,22 @@ int mg_istft_from_magif_f32(const float* magn_phase, int n_clips, int imgs_per_c
                             float* wav, void* ws, size_t ws_bytes, mgStream stream);
 
 /* ------------------------------------------------------------------------------------------
+ * ProGAN 3x3 convolutions (stride 1, pad 1) as tcgen05 implicit GEMMs, NHWC bf16 activations, fp32
+ * accumulation, fp32 master weights [Cout][Cin][3][3] packed to bf16 inside the call.
+ *   replaces nn.Conv2d(3x3) of networks/generator.py:16-22,31-37 and networks/discriminator.py:15-21,26-32
+ *   (+ LeakyReLU generator.py:23,38 / discriminator.py:22,33, PixelNorm layers.py:11-17 and the nearest
+ *   x2 Upsample generator.py:26-29 when the corresponding flag is set).
+ *
+ * x [B][H(/2)][W(/2)][Cin] bf16, y [B][H][W][Cout] bf16; H, W are the OUTPUT dims.
+ * flags: 1 = LeakyReLU(0.2) epilogue, 2 = PixelNorm epilogue (writes inv_norm [B][H][W] fp32 if non-null),
+ *        4 = input is read through a nearest x2 upsampling, 8 = data-gradient mode: `w_f32` is still the
+ *        forward weight [Cfwd_out = Cin][Cfwd_in = Cout][3][3] and y = dL/dx of the forward conv for x = dL/dy.
+ * ---------------------------------------------------------------------------------------- */
+size_t mg_conv3x3_workspace_bytes(int Cin, int Cout);
+int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* y, float* inv_norm,
+                    int B, int H, int W, int Cin, int Cout, int flags, void* ws, size_t ws_bytes, mgStream stream);
+
+/* ------------------------------------------------------------------------------------------
  * Test-only probe of the tcgen05 / TMEM conventions the convolution kernels rely on (one tile).
  * mode 0: A [Ra][K], B [N][K] bf16 (K contiguous);  D[m][n] = sum_k A[row_off + (m/8)*grp_rows + m%8][k] * B[n][k]
  * mode 1: A [K][128], B [K][N] bf16 (M / N contiguous);  D[m][n] = sum_k A[k][m] * B[k][n]

@@ -1,0 +1,338 @@
+// 3x3 / stride 1 / pad 1 convolutions of the ProGAN blocks as tcgen05 implicit GEMMs (sm_100a).
+//
+// Replaces the nn.Conv2d(3x3, s1, p1) calls of reference music_gan/networks/generator.py:16-22,31-37
+// and discriminator.py:15-21,26-32 (cuDNN in the reference) -- forward (fprop), data gradient (dgrad =
+// the same kernel on flipped / transposed weights) and weight gradient (wgrad, conv_wgrad.cu).
+//
+// Layout: activations NHWC bf16 (torch channels_last), fp32 accumulation in TMEM, fp32 master weights
+// packed to bf16 on the fly.
+//
+// One CTA works on output tiles of 16 x 8 pixels of one image (GEMM M = 128):
+//   * producer warps stage the 18 x 10 input halo of the tile ONCE into shared memory in the canonical
+//     no-swizzle UMMA layout [channel chunk][halo position][8 ch] (umma.cuh).  Zero padding, image borders
+//     and the optional nearest 2x upsampling of the input (generator.py:26-29 folded into the read) are
+//     resolved here, so the upsampled tensor never exists in HBM;
+//   * the nine filter taps are nine START ADDRESSES into that halo tile: tap (ky,kx) starts at halo position
+//     ky*10+kx, the 16 tile rows are the sixteen 8-row core-matrix groups, stride byte offset = one halo
+//     row (160 B).  No im2col buffer, every input byte is fetched once per tile;
+//   * weights of the CTA's output-channel slice stay resident in shared memory for the whole launch;
+//   * one thread issues 9 * Cin/16 tcgen05.mma (M128 x N=slice x K16) per tile into one of two TMEM
+//     accumulators; tcgen05.commit releases the halo slot and hands the accumulator to the epilogue warps;
+//   * epilogue warps: tcgen05.ld -> + bias -> LeakyReLU(0.2) -> PixelNorm (per-pixel channel RMS, in fp32,
+//     layers.py:11-17) -> bf16 -> NHWC store.  The thread that owns TMEM lane m owns pixel m of the tile and
+//     sees all its channels, so PixelNorm needs no cross-thread traffic.
+#include "common.cuh"
+#include "umma.cuh"
+#include "conv_common.cuh"
+
+namespace mg {
+using namespace umma;
+
+struct ConvParams {
+    const __nv_bfloat16* x;      // [B][Hin][Win][Cin]
+    const uint4* wpack;          // packed bf16 weights (pack_weights)
+    const float* bias;           // [Cout] or null
+    __nv_bfloat16* y;            // [B][H][W][Cout]
+    float* inv_norm;             // [B][H][W] 1/sqrt(mean_c(v^2)+eps) (pixelnorm, optional)
+    int B, H, W, Hin, Win, Cin, Cout;
+    int upsample, lrelu, pixelnorm;
+    int tiles_x, tiles_y, n_tiles;
+    int Nt, stages, tmem_cols;
+};
+
+constexpr int kConvThreads = 288;   // warps 0-3 epilogue, 4-7 producers, 8 MMA issue + TMEM alloc
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+k_conv3x3(const ConvParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nch = p.Cin >> 3;
+    const int slice = blockIdx.y;
+    const int n0 = slice * p.Nt;
+    const int nt = min(p.Nt, p.Cout - n0);
+
+    uint4* sW = reinterpret_cast<uint4*>(smem);
+    uint4* sA0 = sW + 9 * nch * nt;
+    float* sBias = reinterpret_cast<float*>(sA0 + (size_t)p.stages * nch * kHaloPitch);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + ((nt + 3) & ~3) + 4);
+    bars = reinterpret_cast<uint64_t*>(((uintptr_t)bars + 7) & ~(uintptr_t)7);
+    uint64_t* full_a = bars;          // [2]
+    uint64_t* empty_a = bars + 2;     // [2]
+    uint64_t* tmem_full = bars + 4;   // [2]
+    uint64_t* tmem_empty = bars + 6;  // [2]
+    uint64_t* w_full = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full_a[i], 128); mbar_init(&empty_a[i], 1);
+            mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128);
+        }
+        mbar_init(w_full, 128);
+        mbar_fence_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int acc_stride = p.tmem_cols >> 1;
+
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    if (warp >= 4 && warp < 8) {
+        // ================= producers =================
+        const int pt = tid - 128;
+        {   // resident weights of this slice + bias
+            const uint4* src = p.wpack + (size_t)9 * nch * n0;
+            const int total = 9 * nch * nt;
+            for (int i = pt; i < total; i += 128) sW[i] = __ldg(src + i);
+            for (int i = pt; i < nt; i += 128) sBias[i] = p.bias ? p.bias[n0 + i] : 0.0f;
+            fence_proxy_async();
+            mbar_arrive(w_full);
+        }
+        const int items = kHaloPos * nch;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int slot = it % p.stages;
+            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+            mbar_wait(&empty_a[slot], ph ^ 1u);
+            const int b = tile / tiles_per_img;
+            const int tr = tile - b * tiles_per_img;
+            const int ty0 = (tr / p.tiles_x) * kTileH - 1, tx0 = (tr % p.tiles_x) * kTileW - 1;
+            uint4* dst = sA0 + (size_t)slot * nch * kHaloPitch;
+            const __nv_bfloat16* xb = p.x + (size_t)b * p.Hin * p.Win * p.Cin;
+            for (int i0 = pt; i0 < items; i0 += 128 * 4) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * 128;
+                    v[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if (i < items) {
+                        const int pos = i / nch, c = i - pos * nch;
+                        const int hy = pos / kHaloW, hx = pos - hy * kHaloW;
+                        const int iy = ty0 + hy, ix = tx0 + hx;
+                        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+                            const int sy = p.upsample ? (iy >> 1) : iy, sx = p.upsample ? (ix >> 1) : ix;
+                            v[u] = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)sy * p.Win + sx) * p.Cin) + c);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * 128;
+                    if (i < items) {
+                        const int pos = i / nch, c = i - pos * nch;
+                        dst[c * kHaloPitch + pos] = v[u];
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&full_a[slot]);
+        }
+    } else if (warp == 8) {
+        // ================= MMA issue (whole warp walks the loop, lane 0 issues) =================
+        const uint32_t idesc = instr_desc_bf16(nt, false, false);
+        const uint32_t w0 = smem_u32(sW);
+        mbar_wait(w_full, 0);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int slot = it % p.stages;
+            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+            const int acc = it & 1;
+            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(&full_a[slot], ph);
+            mbar_wait(&tmem_empty[acc], aph ^ 1u);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a0 = smem_u32(sA0 + (size_t)slot * nch * kHaloPitch);
+                const uint32_t d = tmem_base + acc * acc_stride;
+                bool first = true;
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int ky = tap / 3, kx = tap - ky * 3;
+                    for (int kk = 0; kk < (nch >> 1); ++kk) {
+                        const uint64_t da = smem_desc(a0 + (uint32_t)((ky * kHaloW + kx) + kk * 2 * kHaloPitch) * 16u,
+                                                      kHaloPitch * 16u, kHaloW * 16u);
+                        const uint64_t db = smem_desc(w0 + (uint32_t)((tap * nch + 2 * kk) * nt) * 16u, (uint32_t)nt * 16u, 128u);
+                        mma_bf16(d, da, db, idesc, !first);
+                        first = false;
+                    }
+                }
+                mma_commit(&empty_a[slot]);
+                mma_commit(&tmem_full[acc]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================= epilogue =================
+        const int m = tid;                       // TMEM lane == pixel of the tile
+        const int ry = m >> 3, rx = m & 7;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            const int b = tile / tiles_per_img;
+            const int tr = tile - b * tiles_per_img;
+            const int oy = (tr / p.tiles_x) * kTileH + ry, ox = (tr % p.tiles_x) * kTileW + rx;
+            const bool valid = oy < p.H && ox < p.W;
+            mbar_wait(&tmem_full[acc], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(warp * 32) << 16);
+            float scale = 1.0f;
+            if (p.pixelnorm) {
+                float ss = 0.0f;
+                for (int c0 = 0; c0 < nt; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + c0, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float t = v[j] + sBias[c0 + j];
+                        if (p.lrelu) t = t > 0.0f ? t : 0.2f * t;
+                        ss = fmaf(t, t, ss);
+                    }
+                }
+                scale = 1.0f / sqrtf(ss / (float)nt + 1e-8f);
+                if (valid && p.inv_norm) p.inv_norm[((size_t)b * p.H + oy) * p.W + ox] = scale;
+            }
+            __nv_bfloat16* dst = p.y + (((size_t)b * p.H + oy) * p.W + ox) * p.Cout + n0;
+            for (int c0 = 0; c0 < nt; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                tmem_wait_ld();
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float t0 = v[2 * j] + sBias[c0 + 2 * j], t1 = v[2 * j + 1] + sBias[c0 + 2 * j + 1];
+                    if (p.lrelu) { t0 = t0 > 0.0f ? t0 : 0.2f * t0; t1 = t1 > 0.0f ? t1 : 0.2f * t1; }
+                    __nv_bfloat162 h = __floats2bfloat162_rn(t0 * scale, t1 * scale);
+                    pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                if (valid) {
+                    uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+                    d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: fp32 [Cout][Cin][3][3]  ->  bf16 [slice][tap][Cin/8][nt][8]
+//   transpose_flip = 0 (fprop):  B[n = co][k = ci] of tap (ky,kx) = w[co][ci][ky][kx]
+//   transpose_flip = 1 (dgrad):  the data gradient is a 3x3 convolution of dY with
+//                                w'[ci][co][ky][kx] = w[co][ci][2-ky][2-kx]; n runs over ci, k over co.
+//   `n_out`, `k_in` are the GEMM N and K channel counts of the packed operand.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pack_weights(const float* __restrict__ w, int Cout, int Cin, int transpose_flip, int Nt,
+                               __nv_bfloat16* __restrict__ out) {
+    const int n_out = transpose_flip ? Cin : Cout, k_in = transpose_flip ? Cout : Cin;
+    const int nch = k_in >> 3;
+    const int total = 9 * n_out * k_in;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        // destination order: slice, tap, chunk, n_local, e
+        int r = i;
+        const int e = r & 7; r >>= 3;
+        // r indexes (slice, tap, chunk, n_local) with slice-dependent nt: decode by walking slices
+        int slice = 0, base = 0;
+        for (;;) {
+            const int nt = min(Nt, n_out - slice * Nt);
+            const int cnt = 9 * nch * nt;
+            if (r < base + cnt) {
+                const int q = r - base;
+                const int n_local = q % nt, tc = q / nt;
+                const int c = tc % nch, tap = tc / nch;
+                const int n = slice * Nt + n_local, k = 8 * c + e;
+                const int ky = tap / 3, kx = tap % 3;
+                float v;
+                if (!transpose_flip) v = w[(((size_t)n * Cin + k) * 3 + ky) * 3 + kx];
+                else v = w[(((size_t)k * Cin + n) * 3 + (2 - ky)) * 3 + (2 - kx)];
+                out[i] = __float2bfloat16_rn(v);
+                break;
+            }
+            base += cnt; ++slice;
+        }
+    }
+}
+
+struct ConvPlan { int Nt, stages, tmem_cols, n_slices; size_t smem; };
+
+static ConvPlan plan_conv(int Cin, int Cout, bool need_full_n) {
+    const size_t budget = 200 * 1024;
+    const int nch = Cin / 8;
+    ConvPlan pl{};
+    for (int stages = 2; stages >= 1; --stages) {
+        const size_t halo = (size_t)stages * nch * kHaloPitch * 16;
+        for (int Nt = Cout; Nt >= 16; Nt -= 16) {
+            const size_t wbytes = (size_t)9 * nch * Nt * 16;
+            const size_t tot = wbytes + halo + (size_t)(Nt + 8) * 4 + 128;
+            if (tot <= budget) {
+                pl.Nt = Nt; pl.stages = stages; pl.smem = tot;
+                pl.n_slices = (Cout + Nt - 1) / Nt;
+                int cols = 32; while (cols < 2 * Nt) cols <<= 1;
+                pl.tmem_cols = cols;
+                if (need_full_n && Nt != Cout) { pl.Nt = 0; }
+                return pl;
+            }
+        }
+    }
+    pl.Nt = 0;
+    return pl;
+}
+
+}  // namespace mg
+
+using namespace mg;
+
+extern "C" {
+
+size_t mg_conv3x3_workspace_bytes(int Cin, int Cout) {
+    return align_up((size_t)9 * Cin * Cout * 2, 256);
+}
+
+// flags: bit0 LeakyReLU(0.2), bit1 PixelNorm, bit2 input is nearest-upsampled x2 on the fly, bit3 dgrad weights
+int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* y, float* inv_norm,
+                    int B, int H, int W, int Cin, int Cout, int flags, void* ws, size_t ws_bytes, mgStream stream) {
+    if (!x || !w_f32 || !y || !ws) return MG_ERR_BAD_ARG;
+    const bool dgrad = (flags & 8) != 0;
+    // Cin/Cout are those of the GEMM actually run (for dgrad the caller passes Cin = channels of dY, Cout = channels of dX)
+    if (B <= 0 || H <= 0 || W <= 0 || Cin < 16 || Cout < 16 || (Cin & 15) || (Cout & 15) || Cin > 256 || Cout > 256) return MG_ERR_UNSUPPORTED;
+    const bool ups = (flags & 4) != 0;
+    if (ups && ((H | W) & 1)) return MG_ERR_BAD_ARG;
+    if (ws_bytes < mg_conv3x3_workspace_bytes(Cin, Cout)) return MG_ERR_WORKSPACE;
+    const bool pn = (flags & 2) != 0;
+    ConvPlan pl = plan_conv(Cin, Cout, pn);
+    if (pl.Nt == 0) return MG_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        ProfScope ps("k_pack_weights", st);
+        const int total = 9 * Cin * Cout;
+        // w_f32 is [Cout_w][Cin_w][3][3] of the FORWARD convolution; for dgrad the GEMM's K (=Cin here) is the
+        // forward Cout and the GEMM's N (=Cout here) the forward Cin
+        const int fwd_cout = dgrad ? Cin : Cout, fwd_cin = dgrad ? Cout : Cin;
+        k_pack_weights<<<(total + 255) / 256, 256, 0, st>>>(w_f32, fwd_cout, fwd_cin, dgrad ? 1 : 0, pl.Nt, (__nv_bfloat16*)ws);
+    }
+    ConvParams p{};
+    p.x = (const __nv_bfloat16*)x; p.wpack = (const uint4*)ws; p.bias = bias; p.y = (__nv_bfloat16*)y; p.inv_norm = inv_norm;
+    p.B = B; p.H = H; p.W = W; p.Hin = ups ? H / 2 : H; p.Win = ups ? W / 2 : W; p.Cin = Cin; p.Cout = Cout;
+    p.upsample = ups; p.lrelu = flags & 1; p.pixelnorm = pn;
+    p.tiles_x = (W + kTileW - 1) / kTileW; p.tiles_y = (H + kTileH - 1) / kTileH; p.n_tiles = B * p.tiles_x * p.tiles_y;
+    p.Nt = pl.Nt; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
+    static int sm_count = 0;
+    if (!sm_count) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+    cudaFuncSetAttribute(k_conv3x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    const int per_slice = max(1, min(p.n_tiles, sm_count / pl.n_slices > 0 ? sm_count / pl.n_slices : 1));
+    {
+        ProfScope ps(dgrad ? "k_conv3x3_dgrad" : "k_conv3x3_fprop", st);
+        k_conv3x3<<<dim3(per_slice, pl.n_slices), kConvThreads, pl.smem, st>>>(p);
+    }
+    return check_launch("k_conv3x3");
+}
+
+}  // extern "C"

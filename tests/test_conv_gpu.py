@@ -1,0 +1,82 @@
+"""GPU parity of the tcgen05 implicit-GEMM 3x3 convolutions (C ABI mg_conv3x3_bf16 / mg_conv3x3_wgrad_bf16)
+against torch fp32 conv2d on the SAME bf16-rounded operands (so only accumulation order and the final
+bf16 rounding differ): rel-L2 <= 4e-3 (one bf16 rounding of the output is 2^-9 = 2e-3 per element)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _mk(B, C, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, C, H, W, generator=g).cuda().bfloat16().contiguous(memory_format=torch.channels_last)
+
+
+SHAPES = [  # (B, Cin, Cout, H, W)
+    (1, 16, 16, 16, 8), (2, 32, 32, 32, 32), (2, 16, 32, 64, 64), (1, 48, 32, 40, 24), (3, 64, 48, 16, 16),
+    (2, 128, 112, 8, 8), (2, 160, 160, 4, 4), (4, 144, 160, 2, 2), (2, 32, 128, 4, 4), (1, 32, 16, 128, 128),
+]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", SHAPES)
+def test_fprop(B, Cin, Cout, H, W):
+    from musicgan_b200.networks import ops
+    x = _mk(B, Cin, H, W, 1)
+    g = torch.Generator().manual_seed(2)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    y = ops.conv3x3(x, w, b)
+    ref = F.conv2d(x.float(), w.bfloat16().float(), b, padding=1)
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert rel_l2(y, ref) <= 4e-3, rel_l2(y, ref)
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", SHAPES[:7])
+def test_dgrad(B, Cin, Cout, H, W):
+    from musicgan_b200.networks import ops
+    dy = _mk(B, Cout, H, W, 3)
+    g = torch.Generator().manual_seed(4)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).cuda()
+    dx = ops.conv3x3(dy, w, None, dgrad=True)
+    ref = F.conv_transpose2d(dy.float(), w.bfloat16().float(), padding=1)
+    assert dx.shape == ref.shape
+    assert rel_l2(dx, ref) <= 4e-3, rel_l2(dx, ref)
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 32, 32, 16, 16), (1, 48, 32, 32, 16), (2, 128, 128, 4, 4), (2, 32, 16, 64, 64)])
+def test_fused_epilogue_and_upsample(B, Cin, Cout, H, W):
+    """conv3x3(nearest_up2(x)) + bias -> LeakyReLU(0.2) -> PixelNorm == generator.py:26-40 second half of Block."""
+    from musicgan_b200.networks import ops
+    x = _mk(B, Cin, H // 2, W // 2, 5)
+    g = torch.Generator().manual_seed(6)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    fits = 9 * Cin * Cout * 2 <= 120 * 1024
+    if not fits:
+        y = ops.conv3x3(x, w, b, lrelu=True, upsample_in=True)
+        ref = F.leaky_relu(F.conv2d(F.interpolate(x.float(), scale_factor=2.0, mode="nearest"), w.bfloat16().float(), b, padding=1), 0.2)
+        assert rel_l2(y, ref) <= 4e-3
+        return
+    y, inv = ops.conv3x3(x, w, b, lrelu=True, pixelnorm=True, upsample_in=True, want_inv_norm=True)
+    z = F.leaky_relu(F.conv2d(F.interpolate(x.float(), scale_factor=2.0, mode="nearest"), w.bfloat16().float(), b, padding=1), 0.2)
+    ref = z / torch.sqrt(z.pow(2.0).mean(dim=1, keepdim=True) + 1e-8)
+    assert rel_l2(y, ref) <= 4e-3, rel_l2(y, ref)
+    ref_inv = 1.0 / torch.sqrt(z.pow(2.0).mean(dim=1) + 1e-8)
+    assert rel_l2(inv, ref_inv) <= 1e-4
+
+
+def test_rejects_bad_arguments():
+    from musicgan_b200.networks import ops
+    from musicgan_b200._lib import MgError
+    x = _mk(1, 24, 8, 8, 0)       # channels not a multiple of 16
+    w = torch.randn(16, 24, 3, 3).cuda()
+    with pytest.raises(MgError):
+        ops.conv3x3(x, w)
+    with pytest.raises(ValueError):
+        ops.conv3x3(torch.randn(1, 16, 8, 8).cuda().bfloat16(), torch.randn(16, 16, 3, 3).cuda())   # not channels_last
