@@ -128,6 +128,13 @@ size_t mg_conv3x3_workspace_bytes(int Cin, int Cout);
 int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* y, float* inv_norm,
                     int B, int H, int W, int Cin, int Cout, int flags, void* ws, size_t ws_bytes, mgStream stream);
 
+/* Weight gradient of the same convolution: dw[co][ci][ky][kx] += sum_{b,y,x} dy[b][y][x][co] *
+ * xin[b][y+ky-1][x+kx-1][ci]   (xin = x, or x read through a nearest x2 upsampling when upsample_in != 0).
+ * dy [B][H][W][Cout] bf16, x [B][H(/2)][W(/2)][Cin] bf16, dw fp32 [Cout][Cin][3][3] ACCUMULATED (caller zeroes).
+ * `dbias` is reserved (pass NULL). */
+int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, float* dbias,
+                          int B, int H, int W, int Cin, int Cout, int upsample_in, mgStream stream);
+
 /* ------------------------------------------------------------------------------------------
  * Test-only probe of the tcgen05 / TMEM conventions the convolution kernels rely on (one tile).
  * mode 0: A [Ra][K], B [N][K] bf16 (K contiguous);  D[m][n] = sum_k A[row_off + (m/8)*grp_rows + m%8][k] * B[n][k]

@@ -1,0 +1,209 @@
+// Weight gradient of the 3x3 / s1 / p1 convolutions as a tcgen05 GEMM whose reduction runs over PIXELS.
+//
+//   dw[co][ci][ky][kx] = sum_{b,y,x} dy[b][y][x][co] * xin[b][y+ky-1][x+kx-1][ci]
+//
+// (autograd's convolution_backward weight term for the nn.Conv2d of reference networks/generator.py:16-37 and
+// networks/discriminator.py:15-32).  Per 16 x 8 pixel tile both operands are staged once in the canonical
+// no-swizzle layout [channel chunk][pixel][8 ch] and read as MN-major UMMA operands (umma.cuh):
+//   A = dy tile   : M = co (8-channel chunks, SBO = chunk pitch), K = 128 tile pixels (dense, LBO = 128 B)
+//   B = xin halo  : N = ci,                                       K = the same pixels shifted by the tap:
+//                   16 pixels of one MMA = two tile rows -> start (2j+ky)*10+kx, LBO = one halo row (160 B)
+// so per tile 8 MMAs (M128 x N=Cin x K16) per tap accumulate D_tap[co][ci] in TMEM; the accumulators of all
+// tiles of the CTA stay in TMEM (9 taps x Cin columns, split in tap groups when that exceeds 512 columns) and
+// are flushed ONCE at the end with red.global.add.f32.
+#include "common.cuh"
+#include "umma.cuh"
+#include "conv_common.cuh"
+
+namespace mg {
+using namespace umma;
+
+constexpr int kDyPitch = 130;          // pixels per channel chunk of the staged dy tile (128 + 2: bank spread)
+constexpr int kWgradThreads = 288;
+
+struct WgradParams {
+    const __nv_bfloat16* dy;    // [B][H][W][Cout]
+    const __nv_bfloat16* x;     // [B][Hin][Win][Cin]
+    float* dw;                  // [Cout][Cin][3][3], accumulated atomically
+    int B, H, W, Hin, Win, Cin, Cout, upsample;
+    int tiles_x, tiles_y, n_tiles;
+    int taps_per_group, tmem_cols;
+};
+
+__global__ void __launch_bounds__(kWgradThreads, 1)
+k_conv3x3_wgrad(const WgradParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nch_x = p.Cin >> 3;
+    const int tap0 = blockIdx.y * p.taps_per_group;
+    const int ntaps = min(p.taps_per_group, 9 - tap0);
+    const int co0 = blockIdx.z * 128;
+    const int co_n = min(128, p.Cout - co0);
+    const int nch_dy = co_n >> 3;
+
+    // per stage: dy region (16 chunks reserved so that the unused M rows still address this CTA's smem) + x halo
+    const size_t dy_bytes = (size_t)16 * kDyPitch * 16;
+    const size_t x_bytes = (size_t)nch_x * kHaloPitch * 16;
+    const size_t stage_bytes = dy_bytes + x_bytes;
+    unsigned char* stage0 = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
+    uint64_t* full = bars;        // [2]
+    uint64_t* empty = bars + 2;   // [2]
+    uint64_t* done = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    if (warp >= 4 && warp < 8) {
+        // ================= producers =================
+        const int pt = tid - 128;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int slot = it & 1;
+            const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(&empty[slot], ph ^ 1u);
+            const int b = tile / tiles_per_img;
+            const int tr = tile - b * tiles_per_img;
+            const int oy0 = (tr / p.tiles_x) * kTileH, ox0 = (tr % p.tiles_x) * kTileW;
+            uint4* s_dy = reinterpret_cast<uint4*>(stage0 + slot * stage_bytes);
+            uint4* s_x = reinterpret_cast<uint4*>(stage0 + slot * stage_bytes + dy_bytes);
+            // dy tile: 128 pixels x nch_dy chunks (zero outside the image: those pixels must not contribute)
+            const __nv_bfloat16* dyb = p.dy + (size_t)b * p.H * p.W * p.Cout + co0;
+            const int items_dy = 128 * nch_dy;
+            for (int i = pt; i < items_dy; i += 128) {
+                const int pix = i / nch_dy, c = i - pix * nch_dy;
+                const int oy = oy0 + (pix >> 3), ox = ox0 + (pix & 7);
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (oy < p.H && ox < p.W) v = __ldg(reinterpret_cast<const uint4*>(dyb + ((size_t)oy * p.W + ox) * p.Cout) + c);
+                s_dy[c * kDyPitch + pix] = v;
+            }
+            // x halo (same staging as the forward kernel)
+            const __nv_bfloat16* xb = p.x + (size_t)b * p.Hin * p.Win * p.Cin;
+            const int items_x = kHaloPos * nch_x;
+            for (int i0 = pt; i0 < items_x; i0 += 128 * 4) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * 128;
+                    v[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if (i < items_x) {
+                        const int pos = i / nch_x, c = i - pos * nch_x;
+                        const int hy = pos / kHaloW, hx = pos - hy * kHaloW;
+                        const int iy = oy0 - 1 + hy, ix = ox0 - 1 + hx;
+                        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+                            const int sy = p.upsample ? (iy >> 1) : iy, sx = p.upsample ? (ix >> 1) : ix;
+                            v[u] = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)sy * p.Win + sx) * p.Cin) + c);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * 128;
+                    if (i < items_x) {
+                        const int pos = i / nch_x, c = i - pos * nch_x;
+                        s_x[c * kHaloPitch + pos] = v[u];
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&full[slot]);
+        }
+    } else if (warp == 8) {
+        // ================= MMA issue =================
+        const uint32_t idesc = instr_desc_bf16(p.Cin, true, true);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int slot = it & 1;
+            const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(&full[slot], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a0 = smem_u32(stage0 + slot * stage_bytes);
+                const uint32_t b0 = a0 + (uint32_t)dy_bytes;
+                for (int tl = 0; tl < ntaps; ++tl) {
+                    const int tap = tap0 + tl;
+                    const int ky = tap / 3, kx = tap - ky * 3;
+                    const uint32_t d = tmem_base + tl * p.Cin;
+                    for (int j = 0; j < 8; ++j) {
+                        const uint64_t da = smem_desc(a0 + (uint32_t)(16 * j) * 16u, 128u, kDyPitch * 16u);
+                        const uint64_t db = smem_desc(b0 + (uint32_t)((2 * j + ky) * kHaloW + kx) * 16u, kHaloW * 16u, kHaloPitch * 16u);
+                        mma_bf16(d, da, db, idesc, !(it == 0 && j == 0));
+                    }
+                }
+                mma_commit(&empty[slot]);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) mma_commit(done);
+        __syncwarp();
+    } else {
+        // ================= epilogue: one flush of the TMEM accumulators =================
+        const bool any = blockIdx.x < p.n_tiles;
+        mbar_wait(done, 0);
+        tc_fence_after();
+        const int m = tid;      // TMEM lane == local output channel
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int tl = 0; tl < ntaps; ++tl) {
+            const int tap = tap0 + tl;
+            for (int c0 = 0; c0 < p.Cin; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + tl * p.Cin + c0, v);
+                tmem_wait_ld();
+                if (any && m < co_n) {
+                    float* dst = p.dw + ((size_t)(co0 + m) * p.Cin + c0) * 9 + tap;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) atomicAdd(dst + j * 9, v[j]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+}  // namespace mg
+
+using namespace mg;
+
+extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, float* dbias_unused,
+                                     int B, int H, int W, int Cin, int Cout, int upsample_in, mgStream stream) {
+    (void)dbias_unused;
+    if (!dy || !x || !dw) return MG_ERR_BAD_ARG;
+    if (B <= 0 || H <= 0 || W <= 0 || Cin < 16 || Cout < 16 || (Cin & 15) || (Cout & 15) || Cin > 256 || Cout > 256) return MG_ERR_UNSUPPORTED;
+    if (upsample_in && ((H | W) & 1)) return MG_ERR_BAD_ARG;
+    WgradParams p{};
+    p.dy = (const __nv_bfloat16*)dy; p.x = (const __nv_bfloat16*)x; p.dw = dw;
+    p.B = B; p.H = H; p.W = W; p.Hin = upsample_in ? H / 2 : H; p.Win = upsample_in ? W / 2 : W; p.Cin = Cin; p.Cout = Cout;
+    p.upsample = upsample_in ? 1 : 0;
+    p.tiles_x = (W + kTileW - 1) / kTileW; p.tiles_y = (H + kTileH - 1) / kTileH; p.n_tiles = B * p.tiles_x * p.tiles_y;
+    p.taps_per_group = 512 / Cin > 9 ? 9 : 512 / Cin;
+    const int groups = (9 + p.taps_per_group - 1) / p.taps_per_group;
+    int cols = 32; while (cols < p.taps_per_group * Cin) cols <<= 1;
+    p.tmem_cols = cols;
+    const int mblocks = (Cout + 127) / 128;
+    const size_t smem = 2 * ((size_t)16 * kDyPitch * 16 + (size_t)(Cin / 8) * kHaloPitch * 16) + 128;
+    if (smem > 220 * 1024) return MG_ERR_UNSUPPORTED;
+    static int sm_count = 0;
+    if (!sm_count) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+    cudaFuncSetAttribute(k_conv3x3_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int gx = sm_count / (groups * mblocks);
+    gx = gx < 1 ? 1 : gx;
+    gx = gx > p.n_tiles ? p.n_tiles : gx;
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        ProfScope ps("k_conv3x3_wgrad", st);
+        k_conv3x3_wgrad<<<dim3(gx, groups, mblocks), kWgradThreads, smem, st>>>(p);
+    }
+    return check_launch("k_conv3x3_wgrad");
+}

@@ -1,0 +1,38 @@
+"""The two optimisation steps of the reference training loop (train.py:143-175 critic step, :191-214
+generator step) as functions of the drop-in modules; used by `train`, bench.py and the parity tests.
+
+Differences from the reference that do not change any parameter update: the fake batch is
+detached in the critic step (the reference back-propagates into G and then throws those gradients away).
+"""
+from __future__ import annotations
+
+import torch as th
+
+from . import networks
+
+
+def critic_step(gen, disc, optim_disc, z, x_real, alpha: float, eps=None, step: bool = True):
+    with th.no_grad():
+        x_fake = gen(z, alpha)
+    out_real = disc(x_real, alpha)
+    out_fake = disc(x_fake, alpha)
+    disc_loss = networks.wasserstein_discriminator_loss(out_real, out_fake)
+    grad_pen = disc.gradient_penalty(x_real, x_fake, alpha, eps=eps)
+    gen.zero_grad()
+    disc.zero_grad()
+    (disc_loss + grad_pen).backward()
+    if step and optim_disc is not None:
+        optim_disc.step()
+    return disc_loss.detach(), grad_pen.detach(), out_real.detach(), out_fake.detach()
+
+
+def generator_step(gen, disc, optim_gen, z, alpha: float, step: bool = True):
+    x_fake = gen(z, alpha)
+    out_fake = disc(x_fake, alpha)
+    gen_loss = networks.wasserstein_generator_loss(out_fake)
+    gen.zero_grad()
+    disc.zero_grad()
+    gen_loss.backward()
+    if step and optim_gen is not None:
+        optim_gen.step()
+    return gen_loss.detach(), out_fake.detach()

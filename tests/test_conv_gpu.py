@@ -71,6 +71,27 @@ def test_fused_epilogue_and_upsample(B, Cin, Cout, H, W):
     assert rel_l2(inv, ref_inv) <= 1e-4
 
 
+@pytest.mark.parametrize("B,Cin,Cout,H,W", SHAPES)
+def test_wgrad(B, Cin, Cout, H, W):
+    from musicgan_b200.networks import ops
+    x = _mk(B, Cin, H, W, 7)
+    dy = _mk(B, Cout, H, W, 8)
+    dw = ops.conv3x3_wgrad(dy, x)
+    ref = torch.nn.grad.conv2d_weight(x.float(), (Cout, Cin, 3, 3), dy.float(), padding=1)
+    assert dw.shape == ref.shape and dw.dtype == torch.float32
+    assert rel_l2(dw, ref) <= 1e-4, rel_l2(dw, ref)       # fp32 accumulate of exact bf16 products
+
+
+def test_wgrad_upsampled_input():
+    from musicgan_b200.networks import ops
+    x = _mk(2, 48, 16, 8, 9)
+    dy = _mk(2, 32, 32, 16, 10)
+    dw = ops.conv3x3_wgrad(dy, x, upsample_in=True)
+    xin = F.interpolate(x.float(), scale_factor=2.0, mode="nearest")
+    ref = torch.nn.grad.conv2d_weight(xin, (32, 48, 3, 3), dy.float(), padding=1)
+    assert rel_l2(dw, ref) <= 1e-4
+
+
 def test_rejects_bad_arguments():
     from musicgan_b200.networks import ops
     from musicgan_b200._lib import MgError
