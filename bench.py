@@ -250,6 +250,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("MG_BENCH_WORKLOAD", "transform"), choices=["transform", "train"])
     ap.add_argument("--clips", type=int, default=64, help="clips per GPU per step (transform workload)")
+    ap.add_argument("--batch", type=int, default=8, help="samples per GPU per step (train workload)")
     ap.add_argument("--e2e-clips", type=int, default=16)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()

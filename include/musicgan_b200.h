@@ -136,6 +136,27 @@ int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, float* dbias
                           int B, int H, int W, int Cin, int Cout, int upsample_in, mgStream stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Memory-bound layers around the convolutions (pointwise.cu).  "mask" = LeakyReLU(0.2) derivative taken
+ * from the sign of a saved activation tensor (1 where > 0, else 0.2).
+ *
+ * mg_rgb_expand_bf16   2 -> C 1x1 conv: x [B][2][HW] fp32 planes, w [C][2], b [C]|NULL -> y [B][HW][C] bf16 NHWC;
+ *                      mode 0 plain, 1 LeakyReLU(0.2), 2 multiply by mask(mask_src)
+ *                      (MagPhaseLayer, networks/discriminator.py:37-50)
+ * mg_rgb_project_bf16  C -> 2 1x1 conv: a [B][HW][C] bf16 (optionally masked) -> out [B][2][HW] fp32 planes;
+ *                      weight row k, column c at w2[k*row_stride + c*col_stride]; bias [2]|NULL; act 1 = tanh
+ *                      (ToMagnPhaseLayer, networks/generator.py:43-52, and rgb_expand's data gradient)
+ * mg_rgb_wgrad_bf16    gw[c][k] += sum_p (g*mask)[p][c] x[k][p], gb[c] += sum_p (g*mask)[p][c]  (fp32, caller zeroes)
+ * mg_pool2_bf16        AvgPool2d(2,2) on bf16 NHWC (networks/discriminator.py:24,131); adjoint != 0 runs its
+ *                      transpose (each input pixel * 0.25 replicated to a 2x2 block); Ho, Wo = the SMALLER dims
+ * ---------------------------------------------------------------------------------------- */
+int mg_rgb_expand_bf16(const float* x, const float* w, const float* b, const void* mask_src, void* y,
+                       int B, int64_t HW, int C, int mode, mgStream stream);
+int mg_rgb_project_bf16(const void* a, const float* w2, int row_stride, int col_stride, const float* bias, const void* mask_src,
+                        float* out, int B, int64_t HW, int C, int act, mgStream stream);
+int mg_rgb_wgrad_bf16(const void* g, const void* mask_src, const float* x, float* gw, float* gb, int B, int64_t HW, int C, mgStream stream);
+int mg_pool2_bf16(const void* in, void* out, int B, int Ho, int Wo, int C, int adjoint, mgStream stream);
+
+/* ------------------------------------------------------------------------------------------
  * Test-only probe of the tcgen05 / TMEM conventions the convolution kernels rely on (one tile).
  * mode 0: A [Ra][K], B [N][K] bf16 (K contiguous);  D[m][n] = sum_k A[row_off + (m/8)*grp_rows + m%8][k] * B[n][k]
  * mode 1: A [K][128], B [K][N] bf16 (M / N contiguous);  D[m][n] = sum_k A[k][m] * B[k][n]

@@ -1,0 +1,169 @@
+"""bench.py's GAN-training workload (BASELINE config 2): one WGAN-GP iteration of the reference schedule --
+a critic step every iteration and a generator step every 5th (train.py:189) -- at the final 512 x 512 stage,
+batch 8 per GPU, random-init weights, Adam(lr 1e-3, betas (0, 0.9)) updates included.
+
+Multi-GPU: batch-sharded replicas, gradients averaged with one flat-bucket NCCL all-reduce per optimiser step.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import torch as th
+
+FLOP_D_STEP = 121.78e9     # per sample at stage 7: 3 F_G + 12 F_D  (FlopCounterMode on the reference)
+FLOP_G_STEP = 48.71e9      # 3 F_G + 3 F_D
+FLOP_PER_ITER = FLOP_D_STEP + FLOP_G_STEP / 5.0
+
+
+def _build(stage: int, seed: int, device):
+    from . import networks
+    th.manual_seed(seed)
+    gen, disc = networks.Generator(32, 0), networks.Discriminator(7)
+    for _ in range(stage):
+        gen.next_layer(); disc.next_layer()
+    return gen.to(device), disc.to(device)
+
+
+def _allreduce_grads(module, world: int):
+    import torch.distributed as dist
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    if not grads:
+        return
+    flat = th.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat)
+    flat.div_(world)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+def run(args, rank, world, local, timed_region, ClockSampler, peaks):
+    from . import _lib, train_step
+    from .networks import ops
+    dev = th.device("cuda", local)
+    stage, batch, alpha = 7, args.batch, 0.5
+    gen, disc = _build(stage, 0, dev)
+    opt_g = th.optim.Adam(gen.parameters(), lr=1e-3, betas=(0.0, 0.9))
+    opt_d = th.optim.Adam(disc.parameters(), lr=1e-3, betas=(0.0, 0.9))
+    g = th.Generator(device=dev).manual_seed(1000 + rank)
+    res = 4 * 2 ** stage
+    n_real = 4
+    reals_host = [(th.rand(batch, 2, res, res) * 2 - 1).pin_memory() for _ in range(n_real)]
+    reals_dev = [x.to(dev) for x in reals_host]
+    it = [0]
+
+    def one_iter(x_real):
+        z = th.randn(batch, 32, 2, 2, device=dev, generator=g)
+        with th.no_grad():
+            x_fake = gen(z, alpha)
+        out_both = disc(th.cat([x_real, x_fake], dim=0), alpha)
+        d_loss = -(out_both[:batch].mean() - out_both[batch:].mean())
+        gp = disc.gradient_penalty(x_real, x_fake, alpha)
+        gen.zero_grad(); disc.zero_grad()
+        (d_loss + gp).backward()
+        if world > 1:
+            _allreduce_grads(disc, world)
+        opt_d.step()
+        loss = d_loss.detach() + gp.detach()
+        if it[0] % 5 == 0:
+            z = th.randn(batch, 32, 2, 2, device=dev, generator=g)
+            g_loss = -disc(gen(z, alpha), alpha).mean()
+            gen.zero_grad(); disc.zero_grad()
+            g_loss.backward()
+            if world > 1:
+                _allreduce_grads(gen, world)
+            opt_g.step()
+        it[0] += 1
+        return loss
+
+    def step():
+        one_iter(reals_dev[it[0] % n_real])
+
+    _lib.profile_enable(True)
+    ops.FLOPS["count"] = 0.0
+    with ClockSampler(local) as cs:
+        ms = timed_region(step, args.steps, args.warmup, world)
+    prof = _lib.profile_collect(64)
+    _lib.profile_enable(False)
+    conv_flops_timed = ops.FLOPS["count"] * args.steps / max(args.steps + args.warmup, 1)
+    value = world * args.steps / (ms * 1e-3)
+
+    # end to end: real batch from pinned host memory every step, loss read back
+    dev_in = th.empty_like(reals_dev[0])
+    host_loss = th.empty((), dtype=th.float32).pin_memory()
+
+    def e2e_step():
+        dev_in.copy_(reals_host[it[0] % n_real], non_blocking=True)
+        loss = one_iter(dev_in)
+        host_loss.copy_(loss, non_blocking=True)
+
+    e2e_steps = max(5, min(args.steps, 10))
+    ms2 = timed_region(e2e_step, e2e_steps, 1, world)
+    e2e_value = world * e2e_steps / (ms2 * 1e-3)
+
+    if rank != 0:
+        return None
+    pk = peaks()
+    conv_names = ("k_conv3x3_fprop", "k_conv3x3_dgrad", "k_conv3x3_wgrad")
+    conv_ms = sum(prof.get(n, (0.0, 0))[0] for n in conv_names)
+    conv_launches = sum(prof.get(n, (0.0, 0))[1] for n in conv_names)
+    achieved = conv_flops_timed / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    step_tf = batch * FLOP_PER_ITER * args.steps / (ms * 1e-3) / 1e12
+    cpu = cpu_baseline(batch)
+    return {
+        "metric": "GAN train steps/s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "ProGAN WGAN-GP iteration at 512x512 (BASELINE config 2): critic step every iteration + generator "
+                               "step every 5th, Adam updates included, alpha 0.5 (both fade paths)", "batch_per_gpu": batch,
+                   "global_batch": batch * world, "l2": "activations of one step (>1 GB) exceed L2; 4 rotating real batches",
+                   "parallelism": f"dp{world}" + (" flat-bucket NCCL all-reduce" if world > 1 else "")},
+        "clocks": cs.summary(),
+        "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(reals_host[0].numel() * 4), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(sum(c for _, c in prof.values())),
+        "roofline": {"bound": "tensor", "kernel": "k_conv3x3 (fprop+dgrad+wgrad, all layers)", "achieved": achieved, "peak": pk["tf_sus"],
+                     "unit": "TFLOP/s", "frac": achieved / pk["tf_sus"], "peak_source": pk["src"] + " (sustained bf16)", "traffic": None,
+                     "conv_ms_per_step": conv_ms / args.steps, "conv_launches_per_step": conv_launches / args.steps,
+                     "step_algorithmic_tflops": step_tf, "step_frac": step_tf / pk["tf_sus"],
+                     "kernel_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}},
+        "cpu_baseline": cpu,
+    }
+
+
+def cpu_baseline(batch: int):
+    """Oracle port of the reference step body (fp32, all host threads): one critic step + one generator step at
+    512 x 512, batch `batch`; value = 1 / (t_critic + t_generator / 5)."""
+    from oracle import networks_oracle as no
+    th.set_num_threads(os.cpu_count() or 1)
+    stage, alpha = 7, 0.5
+    sd_g, sd_d = no.make_state("gen", stage, 1), no.make_state("disc", stage, 2)
+    g = th.Generator().manual_seed(0)
+    z = th.randn(batch, 32, 2, 2, generator=g)
+    x_real = th.rand(batch, 2, 512, 512, generator=g) * 2 - 1
+    eps = th.rand(batch, 1, 1, 1, generator=g)
+    t0 = time.perf_counter()
+    no.d_step(sd_g, sd_d, z, x_real, eps, alpha, stage)
+    t1 = time.perf_counter()
+    no.g_step(sd_g, sd_d, z, alpha, stage)
+    t2 = time.perf_counter()
+    v = 1.0 / ((t1 - t0) + (t2 - t1) / 5.0)
+    return {"value": v, "unit": "steps/s", "cores": th.get_num_threads(), "kind": "port",
+            "sample": f"1 critic step ({t1 - t0:.1f} s) + 1 generator step ({t2 - t1:.1f} s), batch {batch}, fp32"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return None
+    batch = args.batch
+    cpu = cpu_baseline(batch)
+    return {
+        "impl": "reference", "metric": "GAN train steps/s", "value": cpu["value"], "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": 1, "warmup": 0, "ms_per_step": 1e3 / cpu["value"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ProGAN WGAN-GP iteration at 512x512 (BASELINE config 2) on the host CPU", "batch_per_gpu": batch},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }

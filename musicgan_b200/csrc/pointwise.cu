@@ -1,0 +1,234 @@
+// Memory-bound companions of the convolution kernels (sm_100a, CUDA cores, 16-byte vector accesses):
+//
+//   rgb_expand    2 -> C   1x1 convolution on fp32 NCHW planes -> bf16 NHWC, + bias, + LeakyReLU or a mask
+//                          multiply           (MagPhaseLayer, reference networks/discriminator.py:37-50)
+//   rgb_project   C -> 2   1x1 convolution on bf16 NHWC -> fp32 NCHW planes, + bias, + tanh, optional mask on the
+//                          input            (ToMagnPhaseLayer, networks/generator.py:43-52; and the data gradient
+//                          of rgb_expand)
+//   rgb_wgrad     sum over pixels of (masked) bf16 NHWC tensor (x) fp32 planes -> [C][2] (+ [C]) weight / bias grads
+//   pool2 / unpool2   2x2 average pooling on bf16 NHWC and its adjoint (AvgPool2d(2,2), discriminator.py:24,131)
+//
+// "mask" = LeakyReLU(0.2) derivative recovered from the sign of a saved activation h: 1 where h > 0 else 0.2.
+// The three rgb_* maps are closed under differentiation (each one's derivative w.r.t. either argument is another
+// of the three), which is what the gradient penalty's double backward needs.
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace mg {
+
+__device__ __forceinline__ float lrelu02(float v) { return v > 0.0f ? v : 0.2f * v; }
+
+union Pack8 { uint4 u; __nv_bfloat162 h[4]; };
+
+// ---- 2 -> C ------------------------------------------------------------------------------------
+// x [B][2][HW] fp32, w [C][2], b [C] or null, mask_src [B][HW][C] bf16 or null, y [B][HW][C] bf16
+// mode: 0 none, 1 LeakyReLU(0.2) on the result, 2 multiply the result by mask(mask_src)
+__global__ void __launch_bounds__(256)
+k_rgb_expand(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+             const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y, int64_t HW, int C, int mode, int64_t total) {
+    extern __shared__ float sw[];           // [C][2] then [C] bias
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sw[2 * C + i] = b ? b[i] : 0.0f;
+    __syncthreads();
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t bi = p / HW, q = p - bi * HW;
+        const float x0 = x[(bi * 2) * HW + q], x1 = x[(bi * 2 + 1) * HW + q];
+        uint4* dst = reinterpret_cast<uint4*>(y + p * C);
+        const uint4* msk = mask_src ? reinterpret_cast<const uint4*>(mask_src + p * C) : nullptr;
+        for (int c0 = 0; c0 < C; c0 += 8) {
+            Pack8 o, m;
+            if (mode == 2) m.u = msk[c0 >> 3];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + 2 * j;
+                float v0 = fmaf(sw[2 * c], x0, fmaf(sw[2 * c + 1], x1, sw[2 * C + c]));
+                float v1 = fmaf(sw[2 * c + 2], x0, fmaf(sw[2 * c + 3], x1, sw[2 * C + c + 1]));
+                if (mode == 1) { v0 = lrelu02(v0); v1 = lrelu02(v1); }
+                if (mode == 2) {
+                    const float2 mm = __bfloat1622float2(m.h[j]);
+                    v0 *= mm.x > 0.0f ? 1.0f : 0.2f; v1 *= mm.y > 0.0f ? 1.0f : 0.2f;
+                }
+                o.h[j] = __floats2bfloat162_rn(v0, v1);
+            }
+            dst[c0 >> 3] = o.u;
+        }
+    }
+}
+
+// ---- C -> 2 ------------------------------------------------------------------------------------
+// a [B][HW][C] bf16, w2 = two rows of C weights: row k at w2[k * row_stride + c * col_stride] (so both a [2][C]
+// forward weight and the transpose of a [C][2] weight can be passed), bias [2] or null, mask_src or null,
+// out [B][2][HW] fp32.  act: 0 none, 1 tanh
+__global__ void __launch_bounds__(256)
+k_rgb_project(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w2, int row_stride, int col_stride,
+              const float* __restrict__ bias, const __nv_bfloat16* __restrict__ mask_src, float* __restrict__ out,
+              int64_t HW, int C, int act, int64_t total) {
+    extern __shared__ float sw[];           // [2][C]
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) { const int k = i / C, c = i - k * C; sw[i] = w2[k * row_stride + c * col_stride]; }
+    __syncthreads();
+    const float b0 = bias ? bias[0] : 0.0f, b1 = bias ? bias[1] : 0.0f;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t bi = p / HW, q = p - bi * HW;
+        const uint4* src = reinterpret_cast<const uint4*>(a + p * C);
+        const uint4* msk = mask_src ? reinterpret_cast<const uint4*>(mask_src + p * C) : nullptr;
+        float s0 = b0, s1 = b1;
+        for (int c0 = 0; c0 < C; c0 += 8) {
+            Pack8 v, m;
+            v.u = __ldg(src + (c0 >> 3));
+            if (msk) m.u = __ldg(msk + (c0 >> 3));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = __bfloat1622float2(v.h[j]);
+                if (msk) { const float2 mm = __bfloat1622float2(m.h[j]); f.x *= mm.x > 0.0f ? 1.0f : 0.2f; f.y *= mm.y > 0.0f ? 1.0f : 0.2f; }
+                const int c = c0 + 2 * j;
+                s0 = fmaf(f.x, sw[c], s0); s0 = fmaf(f.y, sw[c + 1], s0);
+                s1 = fmaf(f.x, sw[C + c], s1); s1 = fmaf(f.y, sw[C + c + 1], s1);
+            }
+        }
+        if (act == 1) { s0 = tanhf(s0); s1 = tanhf(s1); }
+        out[(bi * 2) * HW + q] = s0;
+        out[(bi * 2 + 1) * HW + q] = s1;
+    }
+}
+
+// ---- weight / bias gradient of the 1x1 layers ---------------------------------------------------
+// gw[c][0..1] += sum_p g[p][c] * mask * x[b][0..1][q],  gb[c] += sum_p g[p][c] * mask
+// grid (blocks, C/8): each thread owns 8 channels of a strided set of pixels; warp shuffle + atomics
+__global__ void __launch_bounds__(256)
+k_rgb_wgrad(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ mask_src, const float* __restrict__ x,
+            float* __restrict__ gw, float* __restrict__ gb, int64_t HW, int C, int64_t total) {
+    const int c0 = blockIdx.y * 8;
+    float acc[8][3];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = 0.0f;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t bi = p / HW, q = p - bi * HW;
+        const float x0 = x[(bi * 2) * HW + q], x1 = x[(bi * 2 + 1) * HW + q];
+        Pack8 v, m;
+        v.u = __ldg(reinterpret_cast<const uint4*>(g + p * C + c0));
+        if (mask_src) m.u = __ldg(reinterpret_cast<const uint4*>(mask_src + p * C + c0));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = __bfloat1622float2(v.h[j]);
+            if (mask_src) { const float2 mm = __bfloat1622float2(m.h[j]); f.x *= mm.x > 0.0f ? 1.0f : 0.2f; f.y *= mm.y > 0.0f ? 1.0f : 0.2f; }
+            acc[2 * j][0] = fmaf(f.x, x0, acc[2 * j][0]); acc[2 * j][1] = fmaf(f.x, x1, acc[2 * j][1]); acc[2 * j][2] += f.x;
+            acc[2 * j + 1][0] = fmaf(f.y, x0, acc[2 * j + 1][0]); acc[2 * j + 1][1] = fmaf(f.y, x1, acc[2 * j + 1][1]); acc[2 * j + 1][2] += f.y;
+        }
+    }
+    __shared__ float red[8][24];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float v = acc[j][k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[warp][j * 3 + k] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < 24) {
+        float v = 0.0f;
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        const int j = threadIdx.x / 3, k = threadIdx.x % 3;
+        if (k < 2) atomicAdd(&gw[(c0 + j) * 2 + k], v);
+        else if (gb) atomicAdd(&gb[c0 + j], v);
+    }
+}
+
+// ---- 2x2 average pooling, bf16 NHWC ---------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pool2(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int Ho, int Wo, int C8, int64_t total) {
+    // one thread = 8 channels of one output pixel
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8);
+        int64_t r = i / C8;
+        const int ox = (int)(r % Wo); r /= Wo;
+        const int oy = (int)(r % Ho);
+        const int64_t b = r / Ho;
+        const uint4* src = reinterpret_cast<const uint4*>(in) + ((b * 2 * Ho + 2 * oy) * (int64_t)(2 * Wo) + 2 * ox) * C8 + c;
+        Pack8 v00, v01, v10, v11, o;
+        v00.u = __ldg(src); v01.u = __ldg(src + C8);
+        v10.u = __ldg(src + (int64_t)2 * Wo * C8); v11.u = __ldg(src + (int64_t)2 * Wo * C8 + C8);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 a = __bfloat1622float2(v00.h[j]), bb = __bfloat1622float2(v01.h[j]);
+            const float2 cc = __bfloat1622float2(v10.h[j]), d = __bfloat1622float2(v11.h[j]);
+            o.h[j] = __floats2bfloat162_rn(0.25f * ((a.x + bb.x) + (cc.x + d.x)), 0.25f * ((a.y + bb.y) + (cc.y + d.y)));
+        }
+        reinterpret_cast<uint4*>(out)[i] = o.u;
+    }
+}
+
+// adjoint: out[b][2y+i][2x+j][c] = 0.25 * in[b][y][x][c]
+__global__ void __launch_bounds__(256)
+k_unpool2(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int Hi, int Wi, int C8, int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8);
+        int64_t r = i / C8;
+        const int x = (int)(r % Wi); r /= Wi;
+        const int y = (int)(r % Hi);
+        const int64_t b = r / Hi;
+        Pack8 v, o;
+        v.u = __ldg(reinterpret_cast<const uint4*>(in) + i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(v.h[j]); o.h[j] = __floats2bfloat162_rn(0.25f * f.x, 0.25f * f.y); }
+        uint4* dst = reinterpret_cast<uint4*>(out) + ((b * 2 * Hi + 2 * y) * (int64_t)(2 * Wi) + 2 * x) * C8 + c;
+        dst[0] = o.u; dst[C8] = o.u; dst[(int64_t)2 * Wi * C8] = o.u; dst[(int64_t)2 * Wi * C8 + C8] = o.u;
+    }
+}
+
+static unsigned grid_for(int64_t items, int per_block = 256, int cap = 148 * 16) {
+    int64_t g = (items + per_block - 1) / per_block;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace mg
+
+using namespace mg;
+
+extern "C" {
+
+int mg_rgb_expand_bf16(const float* x, const float* w, const float* b, const void* mask_src, void* y,
+                       int B, int64_t HW, int C, int mode, mgStream stream) {
+    if (!x || !w || !y || B <= 0 || HW <= 0 || C < 8 || (C & 7) || C > 512) return MG_ERR_BAD_ARG;
+    if (mode == 2 && !mask_src) return MG_ERR_BAD_ARG;
+    const int64_t total = (int64_t)B * HW;
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope ps("k_rgb_expand", st);
+    k_rgb_expand<<<grid_for(total), 256, 3 * C * sizeof(float), st>>>(x, w, b, (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)y, HW, C, mode, total);
+    return check_launch("k_rgb_expand");
+}
+
+int mg_rgb_project_bf16(const void* a, const float* w2, int row_stride, int col_stride, const float* bias, const void* mask_src,
+                        float* out, int B, int64_t HW, int C, int act, mgStream stream) {
+    if (!a || !w2 || !out || B <= 0 || HW <= 0 || C < 8 || (C & 7) || C > 512) return MG_ERR_BAD_ARG;
+    const int64_t total = (int64_t)B * HW;
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope ps("k_rgb_project", st);
+    k_rgb_project<<<grid_for(total), 256, 2 * C * sizeof(float), st>>>((const __nv_bfloat16*)a, w2, row_stride, col_stride, bias,
+                                                                      (const __nv_bfloat16*)mask_src, out, HW, C, act, total);
+    return check_launch("k_rgb_project");
+}
+
+int mg_rgb_wgrad_bf16(const void* g, const void* mask_src, const float* x, float* gw, float* gb, int B, int64_t HW, int C, mgStream stream) {
+    if (!g || !x || !gw || B <= 0 || HW <= 0 || C < 8 || (C & 7) || C > 512) return MG_ERR_BAD_ARG;
+    const int64_t total = (int64_t)B * HW;
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope ps("k_rgb_wgrad", st);
+    const unsigned gx = grid_for(total, 256 * 8, 148 * 4);
+    k_rgb_wgrad<<<dim3(gx, C / 8), 256, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)mask_src, x, gw, gb, HW, C, total);
+    return check_launch("k_rgb_wgrad");
+}
+
+int mg_pool2_bf16(const void* in, void* out, int B, int Ho, int Wo, int C, int adjoint, mgStream stream) {
+    if (!in || !out || B <= 0 || Ho <= 0 || Wo <= 0 || C < 8 || (C & 7)) return MG_ERR_BAD_ARG;
+    const int64_t total = (int64_t)B * Ho * Wo * (C / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope ps(adjoint ? "k_unpool2" : "k_pool2", st);
+    if (!adjoint) k_pool2<<<grid_for(total), 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, Ho, Wo, C / 8, total);
+    else k_unpool2<<<grid_for(total), 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, Ho, Wo, C / 8, total);
+    return check_launch("k_pool2");
+}
+
+}  // extern "C"

@@ -143,8 +143,110 @@ class GenConv(Function):
         return gx, gw, gb, None
 
 
-def conv1x1(x: th.Tensor, w: th.Tensor, b: th.Tensor) -> th.Tensor:
-    """1x1 convolutions of the to/from magnitude-phase layers (generator.py:46-50, discriminator.py:43-48):
-    K = 2 or N = 2, memory bound, not tensor-core work; bf16 operands, fp32 accumulate, fp32 bias add."""
-    y = F.conv2d(x, w.to(x.dtype))
-    return y.float() + b.float()[None, :, None, None]
+class RgbExpand(Function):
+    """y = (W x + b) -> LeakyReLU(0.2) or mask multiply; x (B,2,H,W) fp32, w (C,2,1,1)|(C,2), y bf16 NHWC.
+    One of the three mutually-differentiating 1x1 maps (RgbExpand / RgbProject / RgbWgrad)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, mask_src, lrelu: bool):
+        y = ops.rgb_expand(x, w, b, mask_src=mask_src, lrelu=lrelu)
+        ctx.save_for_backward(x, w, y if lrelu else mask_src)
+        ctx.has_mask = lrelu or mask_src is not None
+        ctx.w_shape = w.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, m = ctx.saved_tensors
+        m = m if ctx.has_mask else None
+        gx = RgbProject.apply(gy, w, m) if ctx.needs_input_grad[0] else None
+        gw = gb = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            gw, gb = RgbWgrad.apply(gy, m, x)
+            gw = gw.reshape(ctx.w_shape)
+        return gx, gw, gb, None, None
+
+
+class RgbProject(Function):
+    """out = W^T (a * mask): a bf16 NHWC (B,C,H,W), w (C,2,...) -> out fp32 (B,2,H,W)."""
+
+    @staticmethod
+    def forward(ctx, a, w, mask_src):
+        ctx.save_for_backward(a, w, mask_src)
+        ctx.w_shape = w.shape
+        return ops.rgb_project(_act(a), w, mask_src=mask_src, w_is_c_by_2=True)
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, w, m = ctx.saved_tensors
+        ga = RgbExpand.apply(gout, w, None, m, False) if ctx.needs_input_grad[0] else None
+        gw = None
+        if ctx.needs_input_grad[1]:
+            gw, _ = RgbWgrad.apply(a, m, gout)
+            gw = gw.reshape(ctx.w_shape)
+        return ga, gw, None
+
+
+class RgbWgrad(Function):
+    """(gw, gb) = (sum_p (g*mask)[p,c] x[k,p], sum_p (g*mask)[p,c])."""
+
+    @staticmethod
+    def forward(ctx, g, mask_src, x):
+        ctx.save_for_backward(g, mask_src, x)
+        return ops.rgb_wgrad(_act(g), mask_src, x)
+
+    @staticmethod
+    def backward(ctx, ggw, ggb):
+        g, m, x = ctx.saved_tensors
+        gg = RgbExpand.apply(x, ggw, ggb, m, False) if ctx.needs_input_grad[0] else None
+        gx = RgbProject.apply(g, ggw, m) if ctx.needs_input_grad[2] else None
+        return gg, None, gx
+
+
+class ToRgbTanh(Function):
+    """out = tanh(W a + b): a bf16 NHWC, W (2,C,1,1) -> fp32 (B,2,H,W)  (generator.py:46-51).  First order only."""
+
+    @staticmethod
+    def forward(ctx, a, w, b):
+        aa = _act(a)
+        out = ops.rgb_project(aa, w, bias=b, tanh=True)
+        ctx.save_for_backward(aa, w, out)
+        return out
+
+    @staticmethod
+    @th.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        aa, w, out = ctx.saved_tensors
+        gpre = (gout.float() * (1.0 - out * out)).contiguous()
+        ga = gw = gb = None
+        C = aa.shape[1]
+        if ctx.needs_input_grad[0]:
+            ga = ops.rgb_expand(gpre, w.float().reshape(2, C).t().contiguous())
+        if ctx.needs_input_grad[1]:
+            gwt, _ = ops.rgb_wgrad(aa, None, gpre)          # (C, 2)
+            gw = gwt.t().reshape(w.shape).contiguous()
+        if ctx.needs_input_grad[2]:
+            gb = gpre.sum(dim=(0, 2, 3))
+        return ga, gw, gb
+
+
+class Pool2(Function):
+    """AvgPool2d(2, 2) on bf16 NHWC; its backward is the adjoint kernel, whose backward is the pooling again."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.pool2(_act(x))
+
+    @staticmethod
+    def backward(ctx, g):
+        return Unpool2.apply(g)
+
+
+class Unpool2(Function):
+    @staticmethod
+    def forward(ctx, g):
+        return ops.pool2(_act(g), adjoint=True)
+
+    @staticmethod
+    def backward(ctx, gg):
+        return Pool2.apply(gg)

@@ -16,6 +16,7 @@ FLAG_LRELU, FLAG_PIXELNORM, FLAG_UPSAMPLE_IN, FLAG_DGRAD = 1, 2, 4, 8
 
 _declared = False
 _ws_cache = {}
+FLOPS = {"count": 0.0}      # conv FLOPs issued through this module (2 * B*H*W * 9*Cin*Cout per call); bench bookkeeping
 
 
 def _l():
@@ -29,6 +30,11 @@ def _l():
         if hasattr(l, "mg_conv3x3_wgrad_bf16"):
             l.mg_conv3x3_wgrad_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p,
                                                 c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
+        c_int64 = ctypes.c_int64
+        l.mg_rgb_expand_bf16.argtypes = [c_void_p] * 5 + [c_int, c_int64, c_int, c_int, c_void_p]
+        l.mg_rgb_project_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]
+        l.mg_rgb_wgrad_bf16.argtypes = [c_void_p] * 5 + [c_int, c_int64, c_int, c_void_p]
+        l.mg_pool2_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
         _declared = True
     return l
 
@@ -77,6 +83,7 @@ def conv3x3(x: th.Tensor, w: th.Tensor, bias=None, *, lrelu=False, pixelnorm=Fal
     ws = _workspace(x.device, nbytes)
     if bias is not None:
         assert bias.dtype == th.float32 and bias.numel() == cout and bias.is_cuda
+    FLOPS["count"] += 2.0 * B * H * W * 9 * cin * cout
     with th.cuda.device(x.device):
         _lib.check(l.mg_conv3x3_bf16(x.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None,
                                      y.data_ptr(), inv.data_ptr() if inv is not None else None,
@@ -94,8 +101,84 @@ def conv3x3_wgrad(dy: th.Tensor, x: th.Tensor, *, upsample_in=False) -> th.Tenso
     assert x.shape[0] == B and (x.shape[2] * (2 if upsample_in else 1), x.shape[3] * (2 if upsample_in else 1)) == (H, W)
     dw = th.zeros((cout, cin, 3, 3), dtype=th.float32, device=dy.device)
     l = _l()
+    FLOPS["count"] += 2.0 * B * H * W * 9 * cin * cout
     with th.cuda.device(dy.device):
         _lib.check(l.mg_conv3x3_wgrad_bf16(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), None,
                                            B, H, W, cin, cout, 1 if upsample_in else 0,
                                            th.cuda.current_stream().cuda_stream), "mg_conv3x3_wgrad_bf16")
     return dw
+
+
+def _stream():
+    return th.cuda.current_stream().cuda_stream
+
+
+def _planes(x: th.Tensor, name: str) -> th.Tensor:
+    if not (x.is_cuda and x.dim() == 4 and x.shape[1] == 2):
+        raise TypeError(f"{name}: expected a CUDA (B, 2, H, W) tensor, got {tuple(x.shape)} on {x.device}")
+    return x.float().contiguous()
+
+
+def rgb_expand(x: th.Tensor, w: th.Tensor, b=None, mask_src=None, lrelu=False) -> th.Tensor:
+    """(B,2,H,W) fp32 -> (B,C,H,W) bf16 channels_last: W x + b, then LeakyReLU(0.2) or a mask multiply."""
+    x = _planes(x, "rgb_expand x")
+    B, _, H, W = x.shape
+    C = w.shape[0]
+    w = w.float().reshape(C, 2).contiguous()
+    y = th.empty((B, C, H, W), dtype=th.bfloat16, device=x.device, memory_format=th.channels_last)
+    mode = 1 if lrelu else (2 if mask_src is not None else 0)
+    if mask_src is not None:
+        _check_act(mask_src, "rgb_expand mask")
+    with th.cuda.device(x.device):
+        _lib.check(_l().mg_rgb_expand_bf16(x.data_ptr(), w.data_ptr(), b.float().contiguous().data_ptr() if b is not None else None,
+                                           mask_src.data_ptr() if mask_src is not None else None, y.data_ptr(),
+                                           B, H * W, C, mode, _stream()), "mg_rgb_expand_bf16")
+    return y
+
+
+def rgb_project(a: th.Tensor, w: th.Tensor, bias=None, mask_src=None, tanh=False, w_is_c_by_2=False) -> th.Tensor:
+    """(B,C,H,W) bf16 channels_last -> (B,2,H,W) fp32.  `w` is (2,C) (forward ToMagnPhase weight) or, with
+    w_is_c_by_2, a (C,2) weight used transposed (data gradient of rgb_expand)."""
+    _check_act(a, "rgb_project a")
+    B, C, H, W = a.shape
+    w = w.float().reshape(C, 2).contiguous() if w_is_c_by_2 else w.float().reshape(2, C).contiguous()
+    rs, cs = (1, 2) if w_is_c_by_2 else (C, 1)
+    out = th.empty((B, 2, H, W), dtype=th.float32, device=a.device)
+    if mask_src is not None:
+        _check_act(mask_src, "rgb_project mask")
+    with th.cuda.device(a.device):
+        _lib.check(_l().mg_rgb_project_bf16(a.data_ptr(), w.data_ptr(), rs, cs, bias.float().contiguous().data_ptr() if bias is not None else None,
+                                            mask_src.data_ptr() if mask_src is not None else None, out.data_ptr(),
+                                            B, H * W, C, 1 if tanh else 0, _stream()), "mg_rgb_project_bf16")
+    return out
+
+
+def rgb_wgrad(g: th.Tensor, mask_src, x: th.Tensor):
+    """(gw (C,2) fp32, gb (C,) fp32) = sums over pixels of (g * mask) (x) x and of (g * mask)."""
+    _check_act(g, "rgb_wgrad g")
+    x = _planes(x, "rgb_wgrad x")
+    B, C, H, W = g.shape
+    gw = th.zeros((C, 2), dtype=th.float32, device=g.device)
+    gb = th.zeros((C,), dtype=th.float32, device=g.device)
+    if mask_src is not None:
+        _check_act(mask_src, "rgb_wgrad mask")
+    with th.cuda.device(g.device):
+        _lib.check(_l().mg_rgb_wgrad_bf16(g.data_ptr(), mask_src.data_ptr() if mask_src is not None else None, x.data_ptr(),
+                                          gw.data_ptr(), gb.data_ptr(), B, H * W, C, _stream()), "mg_rgb_wgrad_bf16")
+    return gw, gb
+
+
+def pool2(x: th.Tensor, adjoint: bool = False) -> th.Tensor:
+    """AvgPool2d(2,2) on bf16 channels_last, or its adjoint (0.25 * nearest x2 replication)."""
+    _check_act(x, "pool2 x")
+    B, C, H, W = x.shape
+    if adjoint:
+        ho, wo = H, W
+        out = th.empty((B, C, 2 * H, 2 * W), dtype=th.bfloat16, device=x.device, memory_format=th.channels_last)
+    else:
+        assert H % 2 == 0 and W % 2 == 0
+        ho, wo = H // 2, W // 2
+        out = th.empty((B, C, ho, wo), dtype=th.bfloat16, device=x.device, memory_format=th.channels_last)
+    with th.cuda.device(x.device):
+        _lib.check(_l().mg_pool2_bf16(x.data_ptr(), out.data_ptr(), B, ho, wo, C, 1 if adjoint else 0, _stream()), "mg_pool2_bf16")
+    return out

@@ -69,7 +69,7 @@ class ToMagnPhaseLayer(nn.Sequential):
         super().__init__(nn.Conv2d(in_channels, 2, kernel_size=(1, 1), stride=(1, 1)), nn.Tanh())
 
     def forward(self, x: th.Tensor) -> th.Tensor:
-        return th.tanh(fn.conv1x1(x, self[0].weight, self[0].bias))
+        return fn.ToRgbTanh.apply(x, self[0].weight, self[0].bias)
 
 
 class _UpsampledToMagnPhase(nn.Sequential):
@@ -145,7 +145,7 @@ class ConvBlock(nn.Sequential):
 
     def forward(self, x: th.Tensor) -> th.Tensor:
         h = fn.ConvBiasLReLU.apply(x, self[0].weight, self[0].bias)
-        h = F.avg_pool2d(h, 2, 2)
+        h = fn.Pool2.apply(h)
         return fn.ConvBiasLReLU.apply(h, self[3].weight, self[3].bias)
 
 
@@ -156,8 +156,7 @@ class MagPhaseLayer(nn.Sequential):
         super().__init__(nn.Conv2d(2, out_channels, kernel_size=(1, 1), stride=(1, 1)), nn.LeakyReLU(2e-1))
 
     def forward(self, x: th.Tensor) -> th.Tensor:
-        y = F.leaky_relu(fn.conv1x1(fn.ops.as_act(x), self[0].weight, self[0].bias), 2e-1)
-        return fn.ops.as_act(y)
+        return fn.RgbExpand.apply(x, self[0].weight, self[0].bias, None, True)
 
 
 class _PooledMagPhase(nn.Sequential):

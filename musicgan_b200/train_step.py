@@ -14,8 +14,10 @@ from . import networks
 def critic_step(gen, disc, optim_disc, z, x_real, alpha: float, eps=None, step: bool = True):
     with th.no_grad():
         x_fake = gen(z, alpha)
-    out_real = disc(x_real, alpha)
-    out_fake = disc(x_fake, alpha)
+    # the critic has no batch-coupled layer, so D(real) and D(fake) are one pass over the concatenated batch
+    n = x_real.size(0)
+    out_both = disc(th.cat([x_real, x_fake], dim=0), alpha)
+    out_real, out_fake = out_both[:n], out_both[n:]
     disc_loss = networks.wasserstein_discriminator_loss(out_real, out_fake)
     grad_pen = disc.gradient_penalty(x_real, x_fake, alpha, eps=eps)
     gen.zero_grad()

@@ -87,7 +87,7 @@ def gen_forward(sd: SD, z: torch.Tensor, alpha: float, stage: int) -> torch.Tens
     return alpha * new + (1.0 - alpha) * old
 
 
-def disc_forward(sd: SD, x: torch.Tensor, alpha: float, stage: int) -> torch.Tensor:
+def disc_forward(sd: SD, x: torch.Tensor, alpha: float, stage: int, return_features: bool = False) -> torch.Tensor:
     """discriminator.py:107-124 at curr_layer == 7 - stage."""
     def block(h, j):                                             # discriminator.py:14-34
         p = f"_Discriminator__conv_blocks.{j}."
@@ -104,6 +104,8 @@ def disc_forward(sd: SD, x: torch.Tensor, alpha: float, stage: int) -> torch.Ten
         h = alpha * h + (1 - alpha) * old
     for j in range(cur + 1, len(D_CHANNELS)):
         h = block(h, j)
+    if return_features:
+        return h.flatten(1, -1)
     return F.linear(h.flatten(1, -1), sd["_Discriminator__clf.0.weight"], sd["_Discriminator__clf.0.bias"])
 
 

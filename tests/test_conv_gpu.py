@@ -101,3 +101,36 @@ def test_rejects_bad_arguments():
         ops.conv3x3(x, w)
     with pytest.raises(ValueError):
         ops.conv3x3(torch.randn(1, 16, 8, 8).cuda().bfloat16(), torch.randn(16, 16, 3, 3).cuda())   # not channels_last
+
+
+def test_rgb_layers_and_pooling():
+    """1x1 to/from magnitude-phase layers and 2x2 average pooling against torch fp32."""
+    from musicgan_b200.networks import ops
+    torch.backends.cudnn.allow_tf32 = False          # the torch fp32 reference must really be fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(11)
+    B, C, H, W = 2, 48, 24, 40
+    x = (torch.rand(B, 2, H, W, generator=g) * 2 - 1).cuda()
+    w = torch.randn(C, 2, 1, 1, generator=g).cuda()
+    b = torch.randn(C, generator=g).cuda()
+    y = ops.rgb_expand(x, w, b, lrelu=True)
+    ref = F.leaky_relu(F.conv2d(x, w, b), 0.2)
+    assert rel_l2(y, ref) <= 4e-3
+    a = _mk(B, C, H, W, 12)
+    m = _mk(B, C, H, W, 13)
+    w2 = torch.randn(2, C, 1, 1, generator=g).cuda()
+    b2 = torch.randn(2, generator=g).cuda()
+    out = ops.rgb_project(a, w2, bias=b2, tanh=True)
+    assert rel_l2(out, torch.tanh(F.conv2d(a.float(), w2, b2))) <= 1e-5
+    mask = torch.where(m.float() > 0, 1.0, 0.2)
+    out2 = ops.rgb_project(a, w, mask_src=m, w_is_c_by_2=True)
+    assert rel_l2(out2, F.conv_transpose2d(a.float() * mask, w)) <= 1e-5
+    gw, gb = ops.rgb_wgrad(a, m, x)
+    am = a.float() * mask
+    assert rel_l2(gw, torch.einsum("bchw,bkhw->ck", am, x)) <= 1e-4 and rel_l2(gb, am.sum((0, 2, 3))) <= 1e-4
+    y2 = ops.rgb_expand(x, w, None, mask_src=m)
+    assert rel_l2(y2, F.conv2d(x, w) * mask) <= 4e-3
+    p = ops.pool2(a)
+    assert rel_l2(p, F.avg_pool2d(a.float(), 2, 2)) <= 4e-3
+    u = ops.pool2(p, adjoint=True)
+    assert rel_l2(u, F.interpolate(p.float(), scale_factor=2.0, mode="nearest") * 0.25) <= 4e-3
