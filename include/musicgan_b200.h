@@ -125,6 +125,9 @@ int mg_istft_from_magif_f32(const float* magn_phase, int n_clips, int imgs_per_c
  *        forward weight [Cfwd_out = Cin][Cfwd_in = Cout][3][3] and y = dL/dx of the forward conv for x = dL/dy.
  * ---------------------------------------------------------------------------------------- */
 size_t mg_conv3x3_workspace_bytes(int Cin, int Cout);
+/* Pack fp32 weights once (e.g. per optimiser step) into `packed` (>= mg_conv3x3_workspace_bytes); mg_conv3x3_bf16
+ * called with w_f32 == NULL then reads its `ws` argument as such a pre-packed buffer (same Cin, Cout, dgrad). */
+int mg_conv3x3_pack_weights(const float* w_f32, int Cin, int Cout, int dgrad, void* packed, size_t packed_bytes, mgStream stream);
 int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* y, float* inv_norm,
                     int B, int H, int W, int Cin, int Cout, int flags, void* ws, size_t ws_bytes, mgStream stream);
 
@@ -155,6 +158,9 @@ int mg_rgb_project_bf16(const void* a, const float* w2, int row_stride, int col_
                         float* out, int B, int64_t HW, int C, int act, mgStream stream);
 int mg_rgb_wgrad_bf16(const void* g, const void* mask_src, const float* x, float* gw, float* gb, int B, int64_t HW, int C, mgStream stream);
 int mg_pool2_bf16(const void* in, void* out, int B, int Ho, int Wo, int C, int adjoint, mgStream stream);
+/* LeakyReLU(0.2) backward fused with the bias gradient: gz = gy * mask(y) (bf16 NHWC), gb[c] += sum over pixels of gz
+ * (fp32, caller zeroes, may be NULL).  (backward of the Conv2d + LeakyReLU pairs, discriminator.py:15-22,26-33) */
+int mg_lrelu_bwd_bf16(const void* gy, const void* y, void* gz, float* gb, int64_t n_pixels, int C, mgStream stream);
 
 /* ------------------------------------------------------------------------------------------
  * Test-only probe of the tcgen05 / TMEM conventions the convolution kernels rely on (one tile).

@@ -7,4 +7,9 @@ constexpr int kHaloW = kTileW + 2;               // 10
 constexpr int kHaloH = kTileH + 2;               // 18
 constexpr int kHaloPos = kHaloW * kHaloH;        // 180 halo positions
 constexpr int kHaloPitch = 186;                  // positions per channel chunk in smem (== 2 mod 8: spreads banks)
+constexpr int kMaxStages = 4;                    // halo slots in flight per CTA
+
+// i -> (pos, c) with i = pos * nch + c, via a host-computed reciprocal (exact for i * nch < 2^20)
+struct ItemDiv { unsigned magic; int nch; };
+inline ItemDiv make_item_div(int nch) { ItemDiv d; d.magic = ((1u << 20) + nch - 1) / nch; d.nch = nch; return d; }
 }  // namespace mg

@@ -38,6 +38,7 @@ struct ConvParams {
     int upsample, lrelu, pixelnorm;
     int tiles_x, tiles_y, n_tiles;
     int Nt, stages, tmem_cols;
+    ItemDiv idiv;
 };
 
 constexpr int kConvThreads = 288;   // warps 0-3 epilogue, 4-7 producers, 8 MMA issue + TMEM alloc
@@ -56,18 +57,16 @@ k_conv3x3(const ConvParams p) {
     float* sBias = reinterpret_cast<float*>(sA0 + (size_t)p.stages * nch * kHaloPitch);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + ((nt + 3) & ~3) + 4);
     bars = reinterpret_cast<uint64_t*>(((uintptr_t)bars + 7) & ~(uintptr_t)7);
-    uint64_t* full_a = bars;          // [2]
-    uint64_t* empty_a = bars + 2;     // [2]
-    uint64_t* tmem_full = bars + 4;   // [2]
-    uint64_t* tmem_empty = bars + 6;  // [2]
-    uint64_t* w_full = bars + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* full_a = bars;                       // [kMaxStages]
+    uint64_t* empty_a = bars + kMaxStages;         // [kMaxStages]
+    uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint64_t* w_full = tmem_full + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 5);
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&full_a[i], 128); mbar_init(&empty_a[i], 1);
-            mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128);
-        }
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full_a[i], 128); mbar_init(&empty_a[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
         mbar_init(w_full, 128);
         mbar_fence_init();
     }
@@ -100,35 +99,20 @@ k_conv3x3(const ConvParams p) {
             const int b = tile / tiles_per_img;
             const int tr = tile - b * tiles_per_img;
             const int ty0 = (tr / p.tiles_x) * kTileH - 1, tx0 = (tr % p.tiles_x) * kTileW - 1;
-            uint4* dst = sA0 + (size_t)slot * nch * kHaloPitch;
+            const uint32_t dst = smem_u32(sA0 + (size_t)slot * nch * kHaloPitch);
             const __nv_bfloat16* xb = p.x + (size_t)b * p.Hin * p.Win * p.Cin;
-            for (int i0 = pt; i0 < items; i0 += 128 * 4) {
-                uint4 v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u * 128;
-                    v[u] = make_uint4(0u, 0u, 0u, 0u);
-                    if (i < items) {
-                        const int pos = i / nch, c = i - pos * nch;
-                        const int hy = pos / kHaloW, hx = pos - hy * kHaloW;
-                        const int iy = ty0 + hy, ix = tx0 + hx;
-                        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-                            const int sy = p.upsample ? (iy >> 1) : iy, sx = p.upsample ? (ix >> 1) : ix;
-                            v[u] = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)sy * p.Win + sx) * p.Cin) + c);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u * 128;
-                    if (i < items) {
-                        const int pos = i / nch, c = i - pos * nch;
-                        dst[c * kHaloPitch + pos] = v[u];
-                    }
-                }
+            // asynchronous 16-byte copies (zero fill outside the image); nothing is waited for here, so the loads of
+            // up to `stages` tiles are in flight per CTA
+            for (int i = pt; i < items; i += 128) {
+                const int pos = (int)(((unsigned)i * p.idiv.magic) >> 20), c = i - pos * nch;
+                const int hy = (pos * 6554) >> 16, hx = pos - hy * kHaloW;
+                const int iy = ty0 + hy, ix = tx0 + hx;
+                const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                const int sy = p.upsample ? (iy >> 1) : iy, sx = p.upsample ? (ix >> 1) : ix;
+                const void* src = ok ? (const void*)(reinterpret_cast<const uint4*>(xb + ((size_t)sy * p.Win + sx) * p.Cin) + c) : (const void*)p.x;
+                cp_async16(dst + (uint32_t)(c * kHaloPitch + pos) * 16u, src, ok ? 16u : 0u);
             }
-            fence_proxy_async();
-            mbar_arrive(&full_a[slot]);
+            cp_async_arrive(&full_a[slot]);
         }
     } else if (warp == 8) {
         // ================= MMA issue (whole warp walks the loop, lane 0 issues) =================
@@ -143,6 +127,7 @@ k_conv3x3(const ConvParams p) {
             const uint32_t aph = (uint32_t)(it >> 1) & 1u;
             mbar_wait(&full_a[slot], ph);
             mbar_wait(&tmem_empty[acc], aph ^ 1u);
+            fence_proxy_async();      // cp.async-written operands -> tensor-core (async proxy) reads
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t a0 = smem_u32(sA0 + (size_t)slot * nch * kHaloPitch);
@@ -271,8 +256,9 @@ static ConvPlan plan_conv(int Cin, int Cout, bool need_full_n) {
         const size_t halo = (size_t)stages * nch * kHaloPitch * 16;
         for (int Nt = Cout; Nt >= 16; Nt -= 16) {
             const size_t wbytes = (size_t)9 * nch * Nt * 16;
-            const size_t tot = wbytes + halo + (size_t)(Nt + 8) * 4 + 128;
+            size_t tot = wbytes + halo + (size_t)(Nt + 8) * 4 + 256;
             if (tot <= budget) {
+                while (stages < kMaxStages && tot + (size_t)nch * kHaloPitch * 16 <= budget) { ++stages; tot += (size_t)nch * kHaloPitch * 16; }
                 pl.Nt = Nt; pl.stages = stages; pl.smem = tot;
                 pl.n_slices = (Cout + Nt - 1) / Nt;
                 int cols = 32; while (cols < 2 * Nt) cols <<= 1;
@@ -292,6 +278,20 @@ using namespace mg;
 
 extern "C" {
 
+int mg_conv3x3_pack_weights(const float* w_f32, int Cin, int Cout, int dgrad, void* packed, size_t packed_bytes, mgStream stream) {
+    if (!w_f32 || !packed) return MG_ERR_BAD_ARG;
+    if (Cin < 16 || Cout < 16 || (Cin & 15) || (Cout & 15) || Cin > 256 || Cout > 256) return MG_ERR_UNSUPPORTED;
+    if (packed_bytes < (size_t)9 * Cin * Cout * 2) return MG_ERR_WORKSPACE;
+    ConvPlan pl = plan_conv(Cin, Cout, false);
+    if (pl.Nt == 0) return MG_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope ps("k_pack_weights", st);
+    const int total = 9 * Cin * Cout;
+    const int fwd_cout = dgrad ? Cin : Cout, fwd_cin = dgrad ? Cout : Cin;
+    k_pack_weights<<<(total + 255) / 256, 256, 0, st>>>(w_f32, fwd_cout, fwd_cin, dgrad ? 1 : 0, pl.Nt, (__nv_bfloat16*)packed);
+    return check_launch("k_pack_weights");
+}
+
 size_t mg_conv3x3_workspace_bytes(int Cin, int Cout) {
     return align_up((size_t)9 * Cin * Cout * 2, 256);
 }
@@ -299,7 +299,7 @@ size_t mg_conv3x3_workspace_bytes(int Cin, int Cout) {
 // flags: bit0 LeakyReLU(0.2), bit1 PixelNorm, bit2 input is nearest-upsampled x2 on the fly, bit3 dgrad weights
 int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* y, float* inv_norm,
                     int B, int H, int W, int Cin, int Cout, int flags, void* ws, size_t ws_bytes, mgStream stream) {
-    if (!x || !w_f32 || !y || !ws) return MG_ERR_BAD_ARG;
+    if (!x || !y || !ws) return MG_ERR_BAD_ARG;      // w_f32 == NULL: `ws` already holds the packed weights
     const bool dgrad = (flags & 8) != 0;
     // Cin/Cout are those of the GEMM actually run (for dgrad the caller passes Cin = channels of dY, Cout = channels of dX)
     if (B <= 0 || H <= 0 || W <= 0 || Cin < 16 || Cout < 16 || (Cin & 15) || (Cout & 15) || Cin > 256 || Cout > 256) return MG_ERR_UNSUPPORTED;
@@ -310,7 +310,7 @@ int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* 
     ConvPlan pl = plan_conv(Cin, Cout, pn);
     if (pl.Nt == 0) return MG_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    {
+    if (w_f32) {
         ProfScope ps("k_pack_weights", st);
         const int total = 9 * Cin * Cout;
         // w_f32 is [Cout_w][Cin_w][3][3] of the FORWARD convolution; for dgrad the GEMM's K (=Cin here) is the
@@ -324,6 +324,7 @@ int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* 
     p.upsample = ups; p.lrelu = flags & 1; p.pixelnorm = pn;
     p.tiles_x = (W + kTileW - 1) / kTileW; p.tiles_y = (H + kTileH - 1) / kTileH; p.n_tiles = B * p.tiles_x * p.tiles_y;
     p.Nt = pl.Nt; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
+    p.idiv = make_item_div(Cin / 8);
     static int sm_count = 0;
     if (!sm_count) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
     cudaFuncSetAttribute(k_conv3x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);

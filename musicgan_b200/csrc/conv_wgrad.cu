@@ -27,7 +27,8 @@ struct WgradParams {
     float* dw;                  // [Cout][Cin][3][3], accumulated atomically
     int B, H, W, Hin, Win, Cin, Cout, upsample;
     int tiles_x, tiles_y, n_tiles;
-    int taps_per_group, tmem_cols;
+    int taps_per_group, tmem_cols, stages;
+    ItemDiv idiv_x, idiv_dy;
 };
 
 __global__ void __launch_bounds__(kWgradThreads, 1)
@@ -46,14 +47,14 @@ k_conv3x3_wgrad(const WgradParams p) {
     const size_t x_bytes = (size_t)nch_x * kHaloPitch * 16;
     const size_t stage_bytes = dy_bytes + x_bytes;
     unsigned char* stage0 = smem;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
-    uint64_t* full = bars;        // [2]
-    uint64_t* empty = bars + 2;   // [2]
-    uint64_t* done = bars + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;                    // [kMaxStages]
+    uint64_t* empty = bars + kMaxStages;      // [kMaxStages]
+    uint64_t* done = bars + 2 * kMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
         mbar_init(done, 1);
         mbar_fence_init();
     }
@@ -67,65 +68,50 @@ k_conv3x3_wgrad(const WgradParams p) {
     if (warp >= 4 && warp < 8) {
         // ================= producers =================
         const int pt = tid - 128;
+        const unsigned dy_magic = ((1u << 20) + nch_dy - 1) / nch_dy;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-            const int slot = it & 1;
-            const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+            const int slot = it % p.stages;
+            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
             mbar_wait(&empty[slot], ph ^ 1u);
             const int b = tile / tiles_per_img;
             const int tr = tile - b * tiles_per_img;
             const int oy0 = (tr / p.tiles_x) * kTileH, ox0 = (tr % p.tiles_x) * kTileW;
-            uint4* s_dy = reinterpret_cast<uint4*>(stage0 + slot * stage_bytes);
-            uint4* s_x = reinterpret_cast<uint4*>(stage0 + slot * stage_bytes + dy_bytes);
+            const uint32_t s_dy = smem_u32(stage0 + slot * stage_bytes);
+            const uint32_t s_x = s_dy + (uint32_t)dy_bytes;
             // dy tile: 128 pixels x nch_dy chunks (zero outside the image: those pixels must not contribute)
             const __nv_bfloat16* dyb = p.dy + (size_t)b * p.H * p.W * p.Cout + co0;
             const int items_dy = 128 * nch_dy;
             for (int i = pt; i < items_dy; i += 128) {
-                const int pix = i / nch_dy, c = i - pix * nch_dy;
+                const int pix = (int)(((unsigned)i * dy_magic) >> 20), c = i - pix * nch_dy;
                 const int oy = oy0 + (pix >> 3), ox = ox0 + (pix & 7);
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (oy < p.H && ox < p.W) v = __ldg(reinterpret_cast<const uint4*>(dyb + ((size_t)oy * p.W + ox) * p.Cout) + c);
-                s_dy[c * kDyPitch + pix] = v;
+                const bool ok = oy < p.H && ox < p.W;
+                const void* src = ok ? (const void*)(reinterpret_cast<const uint4*>(dyb + ((size_t)oy * p.W + ox) * p.Cout) + c) : (const void*)p.dy;
+                cp_async16(s_dy + (uint32_t)(c * kDyPitch + pix) * 16u, src, ok ? 16u : 0u);
             }
             // x halo (same staging as the forward kernel)
             const __nv_bfloat16* xb = p.x + (size_t)b * p.Hin * p.Win * p.Cin;
             const int items_x = kHaloPos * nch_x;
-            for (int i0 = pt; i0 < items_x; i0 += 128 * 4) {
-                uint4 v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u * 128;
-                    v[u] = make_uint4(0u, 0u, 0u, 0u);
-                    if (i < items_x) {
-                        const int pos = i / nch_x, c = i - pos * nch_x;
-                        const int hy = pos / kHaloW, hx = pos - hy * kHaloW;
-                        const int iy = oy0 - 1 + hy, ix = ox0 - 1 + hx;
-                        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-                            const int sy = p.upsample ? (iy >> 1) : iy, sx = p.upsample ? (ix >> 1) : ix;
-                            v[u] = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)sy * p.Win + sx) * p.Cin) + c);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u * 128;
-                    if (i < items_x) {
-                        const int pos = i / nch_x, c = i - pos * nch_x;
-                        s_x[c * kHaloPitch + pos] = v[u];
-                    }
-                }
+            for (int i = pt; i < items_x; i += 128) {
+                const int pos = (int)(((unsigned)i * p.idiv_x.magic) >> 20), c = i - pos * nch_x;
+                const int hy = (pos * 6554) >> 16, hx = pos - hy * kHaloW;
+                const int iy = oy0 - 1 + hy, ix = ox0 - 1 + hx;
+                const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                const int sy = p.upsample ? (iy >> 1) : iy, sx = p.upsample ? (ix >> 1) : ix;
+                const void* src = ok ? (const void*)(reinterpret_cast<const uint4*>(xb + ((size_t)sy * p.Win + sx) * p.Cin) + c) : (const void*)p.x;
+                cp_async16(s_x + (uint32_t)(c * kHaloPitch + pos) * 16u, src, ok ? 16u : 0u);
             }
-            fence_proxy_async();
-            mbar_arrive(&full[slot]);
+            cp_async_arrive(&full[slot]);
         }
     } else if (warp == 8) {
         // ================= MMA issue =================
         const uint32_t idesc = instr_desc_bf16(p.Cin, true, true);
         int it = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-            const int slot = it & 1;
-            const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+            const int slot = it % p.stages;
+            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
             mbar_wait(&full[slot], ph);
+            fence_proxy_async();
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t a0 = smem_u32(stage0 + slot * stage_bytes);
@@ -192,8 +178,13 @@ extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, f
     int cols = 32; while (cols < p.taps_per_group * Cin) cols <<= 1;
     p.tmem_cols = cols;
     const int mblocks = (Cout + 127) / 128;
-    const size_t smem = 2 * ((size_t)16 * kDyPitch * 16 + (size_t)(Cin / 8) * kHaloPitch * 16) + 128;
-    if (smem > 220 * 1024) return MG_ERR_UNSUPPORTED;
+    const size_t stage_bytes = (size_t)16 * kDyPitch * 16 + (size_t)(Cin / 8) * kHaloPitch * 16;
+    int stages = (int)((200 * 1024) / stage_bytes);
+    stages = stages > kMaxStages ? kMaxStages : stages;
+    if (stages < 1) return MG_ERR_UNSUPPORTED;
+    p.stages = stages;
+    p.idiv_x = make_item_div(Cin / 8);
+    const size_t smem = stages * stage_bytes + 256;
     static int sm_count = 0;
     if (!sm_count) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
     cudaFuncSetAttribute(k_conv3x3_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -178,6 +178,44 @@ k_unpool2(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
     }
 }
 
+// ---- LeakyReLU backward + bias gradient ------------------------------------------------------------
+// gz = gy * mask(y) (bf16 NHWC), gb[c] += sum_pixels gz[.,c].  grid.x blocks x 256 threads; a thread keeps the same
+// 8-channel chunk for all its pixels (grid stride is a multiple of C/8), so its 8 partial sums stay in registers.
+__global__ void __launch_bounds__(256)
+k_lrelu_bwd(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ gz,
+            float* __restrict__ gb, int C8, int64_t total, int64_t stride) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = first; i < total; i += stride) {
+        Pack8 g, m, o;
+        g.u = __ldg(reinterpret_cast<const uint4*>(gy) + i);
+        m.u = __ldg(reinterpret_cast<const uint4*>(y) + i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = __bfloat1622float2(g.h[j]);
+            const float2 mm = __bfloat1622float2(m.h[j]);
+            f.x *= mm.x > 0.0f ? 1.0f : 0.2f; f.y *= mm.y > 0.0f ? 1.0f : 0.2f;
+            o.h[j] = __floats2bfloat162_rn(f.x, f.y);
+            acc[2 * j] += f.x; acc[2 * j + 1] += f.y;
+        }
+        reinterpret_cast<uint4*>(gz)[i] = o.u;
+    }
+    if (gb) {       // block-level reduction in shared memory, then one global atomic per channel per block
+        extern __shared__ float s_gb[];
+        for (int i = threadIdx.x; i < C8 * 8; i += blockDim.x) s_gb[i] = 0.0f;
+        __syncthreads();
+        if (first < total) {
+            const int c0 = (int)(first % C8) * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(&s_gb[c0 + j], acc[j]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < C8 * 8; i += blockDim.x) atomicAdd(&gb[i], s_gb[i]);
+    }
+}
+
 static unsigned grid_for(int64_t items, int per_block = 256, int cap = 148 * 16) {
     int64_t g = (items + per_block - 1) / per_block;
     return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
@@ -219,6 +257,20 @@ int mg_rgb_wgrad_bf16(const void* g, const void* mask_src, const float* x, float
     const unsigned gx = grid_for(total, 256 * 8, 148 * 4);
     k_rgb_wgrad<<<dim3(gx, C / 8), 256, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)mask_src, x, gw, gb, HW, C, total);
     return check_launch("k_rgb_wgrad");
+}
+
+int mg_lrelu_bwd_bf16(const void* gy, const void* y, void* gz, float* gb, int64_t n_pixels, int C, mgStream stream) {
+    if (!gy || !y || !gz || n_pixels <= 0 || C < 8 || (C & 7)) return MG_ERR_BAD_ARG;
+    const int C8 = C / 8;
+    const int64_t total = n_pixels * C8;
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope ps("k_lrelu_bwd", st);
+    // stride = blocks * 256 must be a multiple of C8 so that a thread always meets the same channel chunk
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    while ((blocks * 256) % C8) ++blocks;
+    k_lrelu_bwd<<<(unsigned)blocks, 256, (size_t)C * sizeof(float), st>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y, (__nv_bfloat16*)gz, gb, C8, total, blocks * 256);
+    return check_launch("k_lrelu_bwd");
 }
 
 int mg_pool2_bf16(const void* in, void* out, int B, int Ho, int Wo, int C, int adjoint, mgStream stream) {

@@ -18,6 +18,8 @@ from torch.autograd import Function
 
 from . import ops
 
+import os
+_UNFUSED_LRELU_BWD = bool(os.environ.get("MG_UNFUSED_LRELU_BWD"))
 LRELU_SLOPE = 0.2
 PN_EPS = 1e-8
 
@@ -94,11 +96,31 @@ class ConvBiasLReLU(Function):
     @staticmethod
     def backward(ctx, gy):
         x, w, y = ctx.saved_tensors
-        gz = gy * _lrelu_mask(y)
+        if _UNFUSED_LRELU_BWD:
+            gz = gy * _lrelu_mask(y)
+            gb = gz.float().sum(dim=(0, 2, 3))
+        else:
+            gz, gb = LReLUBwd.apply(gy, y)
         gx = ConvDgrad.apply(gz, w) if ctx.needs_input_grad[0] else None
         gw = ConvWgrad.apply(gz, x) if ctx.needs_input_grad[1] else None
-        gb = gz.float().sum(dim=(0, 2, 3)) if ctx.needs_input_grad[2] else None
-        return gx, gw, gb
+        return gx, gw, (gb if ctx.needs_input_grad[2] else None)
+
+
+class LReLUBwd(Function):
+    """(gz, gb) = (gy * mask(y), sum_pixels gz): one kernel; linear in gy, so its own backward is the same mask
+    multiply (plus the broadcast of the bias-gradient cotangent)."""
+
+    @staticmethod
+    def forward(ctx, gy, y):
+        ctx.save_for_backward(y)
+        gz, gb = ops.lrelu_bwd(gy, y)
+        return gz, gb
+
+    @staticmethod
+    def backward(ctx, ggz, ggb):
+        (y,) = ctx.saved_tensors
+        g = ggz.float() + ggb.float()[None, :, None, None] if ggb is not None else ggz
+        return (_act(g) * _lrelu_mask(y)), None
 
 
 class GenConv(Function):

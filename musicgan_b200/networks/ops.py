@@ -6,6 +6,7 @@ memory -- exactly what the kernels read and write.  Weights are the fp32 master 
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_int, c_size_t, c_void_p
 
 import torch as th
@@ -35,6 +36,8 @@ def _l():
         l.mg_rgb_project_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]
         l.mg_rgb_wgrad_bf16.argtypes = [c_void_p] * 5 + [c_int, c_int64, c_int, c_void_p]
         l.mg_pool2_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
+        l.mg_lrelu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]
+        l.mg_conv3x3_pack_weights.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]
         _declared = True
     return l
 
@@ -46,6 +49,31 @@ def _workspace(dev, nbytes: int) -> th.Tensor:
         ws = th.empty(max(nbytes, 1 << 20), dtype=th.uint8, device=dev)
         _ws_cache[key] = ws
     return ws
+
+
+def _packed_weights(w: th.Tensor, cin: int, cout: int, dgrad: bool):
+    """Packed bf16 copy of a weight tensor, cached ON the parameter object per (version, storage address): parameters
+    change once per optimiser step but are read by several forward / backward kernels.  The cache lives and dies with
+    the Parameter (a global dict keyed by address would hand one model's weights to the next model allocated at the
+    same address).  Temporaries (double-backward operands) are never cached."""
+    if os.environ.get("MG_NO_PACK_CACHE") or not (w.is_leaf and w.requires_grad):
+        return None
+    cache = getattr(w, "_mg_packed", None)
+    if cache is None:
+        cache = {}
+        w._mg_packed = cache
+    stamp = (w._version, w.data_ptr())
+    hit = cache.get(dgrad)
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
+    l = _l()
+    nbytes = l.mg_conv3x3_workspace_bytes(cin, cout)
+    buf = hit[1] if (hit is not None and hit[1].device == w.device) else th.empty(nbytes, dtype=th.uint8, device=w.device)
+    with th.cuda.device(w.device):
+        _lib.check(l.mg_conv3x3_pack_weights(w.data_ptr(), cin, cout, 1 if dgrad else 0, buf.data_ptr(), buf.numel(),
+                                             th.cuda.current_stream().cuda_stream), "mg_conv3x3_pack_weights")
+    cache[dgrad] = (stamp, buf)
+    return buf
 
 
 def _check_act(x: th.Tensor, name: str):
@@ -79,13 +107,16 @@ def conv3x3(x: th.Tensor, w: th.Tensor, bias=None, *, lrelu=False, pixelnorm=Fal
     y = th.empty((B, cout, H, W), dtype=th.bfloat16, device=x.device, memory_format=th.channels_last)
     inv = th.empty((B, H, W), dtype=th.float32, device=x.device) if (pixelnorm and want_inv_norm) else None
     l = _l()
-    nbytes = l.mg_conv3x3_workspace_bytes(cin, cout)
-    ws = _workspace(x.device, nbytes)
+    packed = _packed_weights(w, cin, cout, dgrad)
+    if packed is not None:
+        ws, w_ptr = packed, None
+    else:
+        ws, w_ptr = _workspace(x.device, l.mg_conv3x3_workspace_bytes(cin, cout)), w.data_ptr()
     if bias is not None:
         assert bias.dtype == th.float32 and bias.numel() == cout and bias.is_cuda
     FLOPS["count"] += 2.0 * B * H * W * 9 * cin * cout
     with th.cuda.device(x.device):
-        _lib.check(l.mg_conv3x3_bf16(x.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None,
+        _lib.check(l.mg_conv3x3_bf16(x.data_ptr(), w_ptr, bias.data_ptr() if bias is not None else None,
                                      y.data_ptr(), inv.data_ptr() if inv is not None else None,
                                      B, H, W, cin, cout, flags, ws.data_ptr(), ws.numel(),
                                      th.cuda.current_stream().cuda_stream), "mg_conv3x3_bf16")
@@ -182,3 +213,16 @@ def pool2(x: th.Tensor, adjoint: bool = False) -> th.Tensor:
     with th.cuda.device(x.device):
         _lib.check(_l().mg_pool2_bf16(x.data_ptr(), out.data_ptr(), B, ho, wo, C, 1 if adjoint else 0, _stream()), "mg_pool2_bf16")
     return out
+
+
+def lrelu_bwd(gy: th.Tensor, y: th.Tensor, want_bias_grad: bool = True):
+    """gz = gy * (y > 0 ? 1 : 0.2) and, fused, the bias gradient sum over pixels (fp32)."""
+    gy = as_act(gy)
+    _check_act(y, "lrelu_bwd y")
+    B, C, H, W = y.shape
+    gz = th.empty_like(y)
+    gb = th.zeros((C,), dtype=th.float32, device=y.device) if want_bias_grad else None
+    with th.cuda.device(y.device):
+        _lib.check(_l().mg_lrelu_bwd_bf16(gy.data_ptr(), y.data_ptr(), gz.data_ptr(), gb.data_ptr() if gb is not None else None,
+                                          B * H * W, C, _stream()), "mg_lrelu_bwd_bf16")
+    return gz, gb
