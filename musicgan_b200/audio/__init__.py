@@ -9,4 +9,6 @@ from .functions import (
     ForwardPlan,
 )
 
+from .dataset import AudioDataset
+from .transforms import ChannelMinMaxNorm, ChangeRange
 from .constant import *

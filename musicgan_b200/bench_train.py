@@ -144,6 +144,7 @@ def cpu_baseline(batch: int):
     z = th.randn(batch, 32, 2, 2, generator=g)
     x_real = th.rand(batch, 2, 512, 512, generator=g) * 2 - 1
     eps = th.rand(batch, 1, 1, 1, generator=g)
+    no.d_step(sd_g, sd_d, z[:1], x_real[:1], eps[:1], alpha, stage)      # warm-up (thread pools, allocator) on one sample
     t0 = time.perf_counter()
     no.d_step(sd_g, sd_d, z, x_real, eps, alpha, stage)
     t1 = time.perf_counter()

@@ -1,0 +1,120 @@
+"""Host-side orchestration helpers of the training loop (reference utils.py:14-242): the progressive-growing
+schedule and the periodic checkpoint writer.  The schedule arithmetic (sample counters, growth thresholds, fade-in
+alpha) is integer / scalar host logic and matches the reference exactly; the real-batch transform runs on the GPU."""
+from __future__ import annotations
+
+from os.path import join
+from typing import List
+
+import torch as th
+import torch.nn.functional as F
+
+from . import audio
+
+
+def antialias_bilinear_matrix(in_size: int, out_size: int, device=None) -> th.Tensor:
+    """(out_size, in_size) 1-D resampling matrix of torch's antialiased bilinear interpolation (align_corners=False),
+    i.e. of torchvision's tensor Resize that the reference applies to every real batch (utils.py:70-82): a triangle
+    filter whose support is the scale factor, weights normalised to sum 1.  The 2-D resize is R_h @ x @ R_w^T -- two
+    small GEMMs instead of ATen's gather kernel (which cannot run the 512 -> 4 case on CUDA: shared-memory limit)."""
+    scale = in_size / out_size
+    support = scale if scale >= 1.0 else 1.0
+    inv = 1.0 / scale if scale >= 1.0 else 1.0
+    m = th.zeros(out_size, in_size, dtype=th.float64)
+    for i in range(out_size):
+        center = scale * (i + 0.5)
+        lo = max(0, int(center - support + 0.5))
+        hi = min(in_size, int(center + support + 0.5))
+        j = th.arange(lo, hi, dtype=th.float64)
+        w = (1.0 - ((j - center + 0.5) * inv).abs()).clamp_min(0.0)
+        m[i, lo:hi] = w / w.sum()
+    return m.to(dtype=th.float32, device=device)
+
+
+class Grower:
+    """Sample-count driven growth schedule (utils.py:14-86)."""
+
+    def __init__(self, n_grow: int, fadein_lengths: List[int], train_lengths: List[int]):
+        assert len(fadein_lengths) == n_grow + 1        # +1: the last layer also fades in
+        assert len(train_lengths) == n_grow
+        self._n_grow = n_grow
+        self._curr_grow = 0
+        self._seen = 0                 # samples seen since the start
+        self._seen_in_stage = 0        # samples seen since the last growth
+        self._downscale = 7
+        self._fadein = list(fadein_lengths)
+        acc, self._thresholds = 0, []
+        for n in train_lengths:        # cumulative sums (utils.py:41-45)
+            acc += n
+            self._thresholds.append(acc)
+        self._resize = {}
+        self._norm = audio.ChannelMinMaxNorm()
+        self._range = audio.ChangeRange(-1., 1.)
+
+    def grow(self, viewed_samples: int) -> bool:
+        self._seen += viewed_samples
+        self._seen_in_stage += viewed_samples
+        if self._curr_grow >= self._n_grow:
+            return False
+        if self._thresholds[self._curr_grow] < self._seen:
+            self._seen_in_stage = 0
+            self._curr_grow += 1
+            self._downscale -= 1
+            return True
+        return False
+
+    @property
+    def alpha(self) -> float:
+        return min(1., (1. + self._seen_in_stage) / self._fadein[self._curr_grow])
+
+    @property
+    def curr_grow(self) -> int:
+        return self._curr_grow
+
+    @property
+    def target_size(self) -> int:
+        return 512 // 2 ** self._downscale
+
+    def scale_transform(self, x: th.Tensor) -> th.Tensor:
+        """ChannelMinMaxNorm -> ChangeRange(-1, 1) -> Resize(512 / 2^k) (utils.py:70-82); torchvision's Resize on a
+        tensor is bilinear interpolation with antialiasing, i.e. exactly this F.interpolate call."""
+        x = self._range(self._norm(x))
+        size = self.target_size
+        if x.size(-1) != size or x.size(-2) != size:
+            key = (x.size(-2), x.size(-1), size, str(x.device))
+            if key not in self._resize:
+                self._resize[key] = (antialias_bilinear_matrix(x.size(-2), size, x.device),
+                                     antialias_bilinear_matrix(x.size(-1), size, x.device))
+            r_h, r_w = self._resize[key]
+            x = th.matmul(th.matmul(r_h, x), r_w.t())
+        return x
+
+
+class Saver:
+    """Every `save_every` calls: the four state dicts under the reference's file names (utils.py:118-145, 209-233).
+    The preview PNGs / sounds of the reference (:147-207) need matplotlib and are not part of the hot path."""
+
+    def __init__(self, output_dir: str, save_every: int, rand_channels: int, rand_height: int = 2, rand_width: int = 2):
+        self._dir, self._every = output_dir, save_every
+        self._counter, self._curr_save = 0, 0
+
+    @property
+    def curr_save(self) -> int:
+        return self._curr_save
+
+    @property
+    def save_counter(self) -> int:
+        return self._counter
+
+    def request_save(self, gen, disc, optim_gen, optim_disc, alpha: float) -> bool:
+        if self._counter % self._every == 0:
+            k = self._curr_save
+            th.save(disc.state_dict(), join(self._dir, f"disc_{k}.pt"))
+            th.save(optim_disc.state_dict(), join(self._dir, f"optim_disc_{k}.pt"))
+            th.save(gen.state_dict(), join(self._dir, f"gen_{k}.pt"))
+            th.save(optim_gen.state_dict(), join(self._dir, f"optim_gen_{k}.pt"))
+            self._curr_save += 1
+            self._counter += 1
+            return True
+        self._counter += 1
+        return False
