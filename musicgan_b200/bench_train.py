@@ -46,16 +46,36 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
     dev = th.device("cuda", local)
     stage, batch, alpha = 7, args.batch, 0.5
     gen, disc = _build(stage, 0, dev)
-    opt_g = th.optim.Adam(gen.parameters(), lr=1e-3, betas=(0.0, 0.9))
-    opt_d = th.optim.Adam(disc.parameters(), lr=1e-3, betas=(0.0, 0.9))
-    g = th.Generator(device=dev).manual_seed(1000 + rank)
+    use_graphs = bool(int(os.environ.get("MG_GRAPHS", "1")))
+    opt_g = th.optim.Adam(gen.parameters(), lr=1e-3, betas=(0.0, 0.9), capturable=use_graphs)
+    opt_d = th.optim.Adam(disc.parameters(), lr=1e-3, betas=(0.0, 0.9), capturable=use_graphs)
+    th.cuda.manual_seed(1000 + rank)
+    g = None
     res = 4 * 2 ** stage
     n_real = 4
     reals_host = [(th.rand(batch, 2, res, res) * 2 - 1).pin_memory() for _ in range(n_real)]
     reals_dev = [x.to(dev) for x in reals_host]
     it = [0]
 
+    graphed = None
+    if use_graphs:
+        from .graphed import GraphedSteps
+        graphed = GraphedSteps(gen, disc, opt_g, opt_d, batch, 32, res, alpha,
+                               grad_sync_d=(lambda: _allreduce_grads(disc, world)) if world > 1 else None,
+                               grad_sync_g=(lambda: _allreduce_grads(gen, world)) if world > 1 else None)
+
+    def graphed_iter(x_real):
+        stats = graphed.critic_step(x_real)
+        loss = stats[0] + stats[1]
+        if it[0] % 5 == 0:
+            graphed.generator_step()
+        it[0] += 1
+        return loss
+
     def one_iter(x_real):
+        nonlocal graphed
+        if graphed is not None:
+            return graphed_iter(x_real)
         z = th.randn(batch, 32, 2, 2, device=dev, generator=g)
         with th.no_grad():
             x_fake = gen(z, alpha)
@@ -82,13 +102,26 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
     def step():
         one_iter(reals_dev[it[0] % n_real])
 
-    _lib.profile_enable(True)
-    ops.FLOPS["count"] = 0.0
     with ClockSampler(local) as cs:
         ms = timed_region(step, args.steps, args.warmup, world)
+    # per-kernel durations and FLOP bookkeeping: graph replays cannot carry event pairs, so the SAME iteration schedule is
+    # run eagerly (5 iterations = 5 critic steps + 1 generator step) with the library's event profiler switched on
+    saved, graphed = graphed, None
+    prof_iters = 5
+    it[0] = 0
+    step(); th.cuda.synchronize()
+    it[0] = 0
+    _lib.profile_enable(True)
+    ops.FLOPS["count"] = 0.0
+    for _ in range(prof_iters):
+        step()
+    th.cuda.synchronize()
     prof = _lib.profile_collect(64)
     _lib.profile_enable(False)
-    conv_flops_timed = ops.FLOPS["count"] * args.steps / max(args.steps + args.warmup, 1)
+    graphed = saved
+    scale = args.steps / prof_iters
+    prof = {k: (v[0] * scale, int(round(v[1] * scale))) for k, v in prof.items()}
+    conv_flops_timed = ops.FLOPS["count"] * scale
     value = world * args.steps / (ms * 1e-3)
 
     # end to end: real batch from pinned host memory every step, loss read back
@@ -120,12 +153,15 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
         "config": {"workload": "ProGAN WGAN-GP iteration at 512x512 (BASELINE config 2): critic step every iteration + generator "
                                "step every 5th, Adam updates included, alpha 0.5 (both fade paths)", "batch_per_gpu": batch,
                    "global_batch": batch * world, "l2": "activations of one step (>1 GB) exceed L2; 4 rotating real batches",
-                   "parallelism": f"dp{world}" + (" flat-bucket NCCL all-reduce" if world > 1 else "")},
+                   "parallelism": f"dp{world}" + (" flat-bucket NCCL all-reduce" if world > 1 else ""),
+                   "cuda_graphs": use_graphs},
         "clocks": cs.summary(),
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(reals_host[0].numel() * 4), "d2h_bytes_per_step": 4},
         "gpu_launches": int(sum(c for _, c in prof.values())),
         "roofline": {"bound": "tensor", "kernel": "k_conv3x3 (fprop+dgrad+wgrad, all layers)", "achieved": achieved, "peak": pk["tf_sus"],
                      "unit": "TFLOP/s", "frac": achieved / pk["tf_sus"], "peak_source": pk["src"] + " (sustained bf16)", "traffic": None,
+                     "kernel_timing": "event pairs around every library kernel in an eager pass of the same 5-iteration schedule "
+                                      "right after the timed region (graph replays cannot carry event pairs)" if use_graphs else "timed region",
                      "conv_ms_per_step": conv_ms / args.steps, "conv_launches_per_step": conv_launches / args.steps,
                      "step_algorithmic_tflops": step_tf, "step_frac": step_tf / pk["tf_sus"],
                      "kernel_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}},

@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include "conv_common.cuh"
+#include <cstdlib>
 
 namespace mg {
 using namespace umma;
@@ -37,13 +38,22 @@ struct ConvParams {
     int B, H, W, Hin, Win, Cin, Cout;
     int upsample, lrelu, pixelnorm;
     int tiles_x, tiles_y, n_tiles;
-    int Nt, stages, tmem_cols;
+    int Nt, stages, tmem_cols, tiles_per_img;
     ItemDiv idiv;
+    FastDiv div_img, div_tx;
+    int consumer_fence;
+    int epi_warps;               // 4 or 8 epilogue warps; producers are the next 4 warps, then the MMA warp
 };
 
-constexpr int kConvThreads = 288;   // warps 0-3 epilogue, 4-7 producers, 8 MMA issue + TMEM alloc
+// warp roles: [0, E) epilogue (E = 4, or 8 = two per TMEM lane quarter with half the columns each), [E, E+4) producers,
+// warp E+4 MMA issue + TMEM alloc.  Block size (E + 5) * 32.
+constexpr int kConvThreads = 13 * 32;                // upper bound (E = 8)
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(kConvThreads, 2)
 k_conv3x3(const ConvParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -51,12 +61,13 @@ k_conv3x3(const ConvParams p) {
     const int slice = blockIdx.y;
     const int n0 = slice * p.Nt;
     const int nt = min(p.Nt, p.Cout - n0);
+    const int kEpiWarps = p.epi_warps, kProdWarp0 = kEpiWarps, kMmaWarp = kEpiWarps + 4;
 
     uint4* sW = reinterpret_cast<uint4*>(smem);
     uint4* sA0 = sW + 9 * nch * nt;
-    float* sBias = reinterpret_cast<float*>(sA0 + (size_t)p.stages * nch * kHaloPitch);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + ((nt + 3) & ~3) + 4);
-    bars = reinterpret_cast<uint64_t*>(((uintptr_t)bars + 7) & ~(uintptr_t)7);
+    float* sBias = reinterpret_cast<float*>(sA0 + (size_t)p.stages * nch * kHaloPitch);      // 16-byte aligned
+    float* sPart = sBias + ((nt + 3) & ~3);                                                  // [2][128] PixelNorm partial sums
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + 256);
     uint64_t* full_a = bars;                       // [kMaxStages]
     uint64_t* empty_a = bars + kMaxStages;         // [kMaxStages]
     uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]
@@ -66,22 +77,20 @@ k_conv3x3(const ConvParams p) {
 
     if (tid == 0) {
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full_a[i], 128); mbar_init(&empty_a[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps * 32); }
         mbar_init(w_full, 128);
         mbar_fence_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, p.tmem_cols);
+    if (warp == kMmaWarp) tmem_alloc(tmem_slot, p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int acc_stride = p.tmem_cols >> 1;
 
-    const int tiles_per_img = p.tiles_x * p.tiles_y;
-
-    if (warp >= 4 && warp < 8) {
+    if (warp >= kProdWarp0 && warp < kMmaWarp) {
         // ================= producers =================
-        const int pt = tid - 128;
+        const int pt = tid - kProdWarp0 * 32;
         {   // resident weights of this slice + bias
             const uint4* src = p.wpack + (size_t)9 * nch * n0;
             const int total = 9 * nch * nt;
@@ -91,121 +100,173 @@ k_conv3x3(const ConvParams p) {
             mbar_arrive(w_full);
         }
         const int items = kHaloPos * nch;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-            const int slot = it % p.stages;
-            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        // Per-thread item table, built once: for each 16-byte chunk this thread copies per tile, where it comes from
+        // relative to the tile origin (tile independent, because tiles start at even rows / columns), where it goes in
+        // the halo slot, and its halo coordinates (for the image-border test).  Up to kItemRegs items live in registers;
+        // wider layers (Cin > 64) take the generic path for the remaining items.
+        constexpr int kItemRegs = 12;
+        int rel[kItemRegs];            // source offset in uint4 units from the tile origin
+        uint32_t dsto[kItemRegs];      // (hy << 24) | (hx << 16) | smem chunk index
+        const int sy_step = p.upsample ? kTileH / 2 : kTileH, sx_step = p.upsample ? kTileW / 2 : kTileW;
+#pragma unroll
+        for (int k = 0; k < kItemRegs; ++k) {
+            const int i = pt + k * 128;
+            rel[k] = 0; dsto[k] = 0xFFFFFFFFu;
+            if (i < items) {
+                const int pos = (int)(((unsigned)i * p.idiv.magic) >> 20), c = i - pos * nch;
+                const int hy = (pos * 6554) >> 16, hx = pos - hy * kHaloW;
+                const int ry = p.upsample ? ((hy - 1) >> 1) : hy - 1, rx = p.upsample ? ((hx - 1) >> 1) : hx - 1;
+                rel[k] = (ry * p.Win + rx) * nch + c;
+                dsto[k] = ((uint32_t)hy << 24) | ((uint32_t)hx << 16) | (uint32_t)(c * kHaloPitch + pos);
+            }
+        }
+        int slot = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             mbar_wait(&empty_a[slot], ph ^ 1u);
-            const int b = tile / tiles_per_img;
-            const int tr = tile - b * tiles_per_img;
-            const int ty0 = (tr / p.tiles_x) * kTileH - 1, tx0 = (tr % p.tiles_x) * kTileW - 1;
+            const int b = fast_div(tile, p.div_img);
+            const int tr = tile - b * p.tiles_per_img;
+            const int tyi = fast_div(tr, p.div_tx), txi = tr - tyi * p.tiles_x;
+            const int ty0 = tyi * kTileH - 1, tx0 = txi * kTileW - 1;
             const uint32_t dst = smem_u32(sA0 + (size_t)slot * nch * kHaloPitch);
-            const __nv_bfloat16* xb = p.x + (size_t)b * p.Hin * p.Win * p.Cin;
+            const uint4* img = reinterpret_cast<const uint4*>(p.x + (size_t)b * p.Hin * p.Win * p.Cin);
+            const uint4* org = img + ((size_t)(tyi * sy_step) * p.Win + txi * sx_step) * nch;
             // asynchronous 16-byte copies (zero fill outside the image); nothing is waited for here, so the loads of
             // up to `stages` tiles are in flight per CTA
-            for (int i = pt; i < items; i += 128) {
+#pragma unroll
+            for (int k = 0; k < kItemRegs; ++k) {
+                if (dsto[k] != 0xFFFFFFFFu) {
+                    const int iy = ty0 + (int)(dsto[k] >> 24), ix = tx0 + (int)((dsto[k] >> 16) & 0xFF);
+                    const bool ok = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+                    cp_async16(dst + (dsto[k] & 0xFFFFu) * 16u, ok ? (const void*)(org + rel[k]) : (const void*)img, ok ? 16u : 0u);
+                }
+            }
+            for (int i = pt + kItemRegs * 128; i < items; i += 128) {
                 const int pos = (int)(((unsigned)i * p.idiv.magic) >> 20), c = i - pos * nch;
                 const int hy = (pos * 6554) >> 16, hx = pos - hy * kHaloW;
                 const int iy = ty0 + hy, ix = tx0 + hx;
-                const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                const bool ok = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
                 const int sy = p.upsample ? (iy >> 1) : iy, sx = p.upsample ? (ix >> 1) : ix;
-                const void* src = ok ? (const void*)(reinterpret_cast<const uint4*>(xb + ((size_t)sy * p.Win + sx) * p.Cin) + c) : (const void*)p.x;
-                cp_async16(dst + (uint32_t)(c * kHaloPitch + pos) * 16u, src, ok ? 16u : 0u);
+                cp_async16(dst + (uint32_t)(c * kHaloPitch + pos) * 16u,
+                           ok ? (const void*)(img + ((size_t)sy * p.Win + sx) * nch + c) : (const void*)img, ok ? 16u : 0u);
             }
             cp_async_arrive(&full_a[slot]);
+            if (++slot == p.stages) { slot = 0; ph ^= 1u; }
         }
-    } else if (warp == 8) {
+    } else if (warp == kMmaWarp) {
         // ================= MMA issue (whole warp walks the loop, lane 0 issues) =================
+        // Descriptors only differ in their 14-bit start-address field, so they are formed by integer additions:
+        //   A: slot base + tap offset (ky*10 + kx positions) + k-step * 2 * kHaloPitch      (16-byte units)
+        //   B: weights are packed [tap][k chunk][n] -> the descriptor simply advances by 2*nt per MMA
         const uint32_t idesc = instr_desc_bf16(nt, false, false);
-        const uint32_t w0 = smem_u32(sW);
+        const uint64_t a_desc0 = smem_desc(smem_u32(sA0), kHaloPitch * 16u, kHaloW * 16u);
+        const uint64_t b_desc0 = smem_desc(smem_u32(sW), (uint32_t)nt * 16u, 128u);
+        const uint32_t slot_units = (uint32_t)(nch * kHaloPitch), b_step = (uint32_t)(2 * nt);
+        const int ksteps = nch >> 1;
         mbar_wait(w_full, 0);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-            const int slot = it % p.stages;
-            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-            const int acc = it & 1;
-            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-            mbar_wait(&full_a[slot], ph);
+        int slot = 0, acc = 0; uint32_t ph = 0, aph = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             mbar_wait(&tmem_empty[acc], aph ^ 1u);
-            fence_proxy_async();      // cp.async-written operands -> tensor-core (async proxy) reads
+            mbar_wait(&full_a[slot], ph);
+            if (p.consumer_fence) fence_proxy_async();      // (debug switch) cp.async-written operands -> async proxy
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t a0 = smem_u32(sA0 + (size_t)slot * nch * kHaloPitch);
                 const uint32_t d = tmem_base + acc * acc_stride;
-                bool first = true;
+                const uint64_t da_slot = a_desc0 + (uint64_t)(slot * slot_units);
+                uint64_t db = b_desc0;
+                uint32_t accum = 0;
+#pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
-                    const int ky = tap / 3, kx = tap - ky * 3;
-                    for (int kk = 0; kk < (nch >> 1); ++kk) {
-                        const uint64_t da = smem_desc(a0 + (uint32_t)((ky * kHaloW + kx) + kk * 2 * kHaloPitch) * 16u,
-                                                      kHaloPitch * 16u, kHaloW * 16u);
-                        const uint64_t db = smem_desc(w0 + (uint32_t)((tap * nch + 2 * kk) * nt) * 16u, (uint32_t)nt * 16u, 128u);
-                        mma_bf16(d, da, db, idesc, !first);
-                        first = false;
+                    uint64_t da = da_slot + (uint64_t)((tap / 3) * kHaloW + (tap % 3));
+                    for (int kk = 0; kk < ksteps; ++kk) {
+                        mma_bf16(d, da, db, idesc, accum);
+                        accum = 1;
+                        da += 2 * kHaloPitch;
+                        db += b_step;
                     }
                 }
                 mma_commit(&empty_a[slot]);
                 mma_commit(&tmem_full[acc]);
             }
             __syncwarp();
+            if (++slot == p.stages) { slot = 0; ph ^= 1u; }
+            if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
     } else {
-        // ================= epilogue =================
-        const int m = tid;                       // TMEM lane == pixel of the tile
+        // ================= epilogue: 8 warps; warp = (half << 2) | quarter =================
+        const int quarter = warp & 3, half = warp >> 2;
+        const int m = quarter * 32 + lane;           // TMEM lane == pixel of the tile
         const int ry = m >> 3, rx = m & 7;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-            const int b = tile / tiles_per_img;
-            const int tr = tile - b * tiles_per_img;
-            const int oy = (tr / p.tiles_x) * kTileH + ry, ox = (tr % p.tiles_x) * kTileW + rx;
+        // columns of this half, in units of 16: the first half takes the larger share
+        const int units = nt >> 4;
+        const bool split = kEpiWarps == 8;
+        const int u0 = (!split || half == 0) ? 0 : (units + 1) >> 1, u1 = !split ? units : (half == 0 ? (units + 1) >> 1 : units);
+        const float inv_c = 1.0f / (float)nt;
+        int acc = 0; uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int b = fast_div(tile, p.div_img);
+            const int tr = tile - b * p.tiles_per_img;
+            const int tyi = fast_div(tr, p.div_tx), txi = tr - tyi * p.tiles_x;
+            const int oy = tyi * kTileH + ry, ox = txi * kTileW + rx;
             const bool valid = oy < p.H && ox < p.W;
             mbar_wait(&tmem_full[acc], aph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(warp * 32) << 16);
+            const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(quarter * 32) << 16);
             float scale = 1.0f;
             if (p.pixelnorm) {
                 float ss = 0.0f;
-                for (int c0 = 0; c0 < nt; c0 += 16) {
+                for (int u = u0; u < u1; ++u) {
                     float v[16];
-                    tmem_ld16(taddr + c0, v);
+                    tmem_ld16(taddr + u * 16, v);
                     tmem_wait_ld();
+                    const float4* b4 = reinterpret_cast<const float4*>(sBias + u * 16);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float t = v[j] + sBias[c0 + j];
-                        if (p.lrelu) t = t > 0.0f ? t : 0.2f * t;
-                        ss = fmaf(t, t, ss);
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 bb = b4[j];
+                        float t0 = v[4 * j] + bb.x, t1 = v[4 * j + 1] + bb.y, t2 = v[4 * j + 2] + bb.z, t3 = v[4 * j + 3] + bb.w;
+                        if (p.lrelu) { t0 = fmaxf(t0, 0.2f * t0); t1 = fmaxf(t1, 0.2f * t1); t2 = fmaxf(t2, 0.2f * t2); t3 = fmaxf(t3, 0.2f * t3); }
+                        ss = fmaf(t0, t0, ss); ss = fmaf(t1, t1, ss); ss = fmaf(t2, t2, ss); ss = fmaf(t3, t3, ss);
                     }
                 }
-                scale = 1.0f / sqrtf(ss / (float)nt + 1e-8f);
-                if (valid && p.inv_norm) p.inv_norm[((size_t)b * p.H + oy) * p.W + ox] = scale;
+                float tot = ss;
+                if (split) {
+                    sPart[half * 128 + m] = ss;
+                    named_bar_sync(1 + quarter, 64);              // the two warps that share this TMEM lane quarter
+                    tot = sPart[m] + sPart[128 + m];
+                    named_bar_sync(1 + quarter, 64);              // sPart may be overwritten by the next tile
+                }
+                scale = 1.0f / sqrtf(tot * inv_c + 1e-8f);
+                if (valid && half == 0 && p.inv_norm) p.inv_norm[((size_t)b * p.H + oy) * p.W + ox] = scale;
             }
             __nv_bfloat16* dst = p.y + (((size_t)b * p.H + oy) * p.W + ox) * p.Cout + n0;
-            for (int c0 = 0; c0 < nt; c0 += 16) {
+            for (int u = u0; u < u1; ++u) {
                 float v[16];
-                tmem_ld16(taddr + c0, v);
+                tmem_ld16(taddr + u * 16, v);
                 tmem_wait_ld();
+                const float4* b4 = reinterpret_cast<const float4*>(sBias + u * 16);
                 uint32_t pk[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float t0 = v[2 * j] + sBias[c0 + 2 * j], t1 = v[2 * j + 1] + sBias[c0 + 2 * j + 1];
-                    if (p.lrelu) { t0 = t0 > 0.0f ? t0 : 0.2f * t0; t1 = t1 > 0.0f ? t1 : 0.2f * t1; }
-                    __nv_bfloat162 h = __floats2bfloat162_rn(t0 * scale, t1 * scale);
-                    pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                for (int j = 0; j < 4; ++j) {
+                    const float4 bb = b4[j];
+                    float t0 = v[4 * j] + bb.x, t1 = v[4 * j + 1] + bb.y, t2 = v[4 * j + 2] + bb.z, t3 = v[4 * j + 3] + bb.w;
+                    if (p.lrelu) { t0 = fmaxf(t0, 0.2f * t0); t1 = fmaxf(t1, 0.2f * t1); t2 = fmaxf(t2, 0.2f * t2); t3 = fmaxf(t3, 0.2f * t3); }
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(t0 * scale, t1 * scale), h1 = __floats2bfloat162_rn(t2 * scale, t3 * scale);
+                    pk[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
+                    pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
                 }
                 if (valid) {
-                    uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+                    uint4* d4 = reinterpret_cast<uint4*>(dst + u * 16);
                     d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 }
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, p.tmem_cols);
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -246,7 +307,7 @@ __global__ void k_pack_weights(const float* __restrict__ w, int Cout, int Cin, i
     }
 }
 
-struct ConvPlan { int Nt, stages, tmem_cols, n_slices; size_t smem; };
+struct ConvPlan { int Nt, stages, tmem_cols, n_slices, occupancy, epi_warps; size_t smem; };
 
 static ConvPlan plan_conv(int Cin, int Cout, bool need_full_n) {
     const size_t budget = 200 * 1024;
@@ -256,9 +317,23 @@ static ConvPlan plan_conv(int Cin, int Cout, bool need_full_n) {
         const size_t halo = (size_t)stages * nch * kHaloPitch * 16;
         for (int Nt = Cout; Nt >= 16; Nt -= 16) {
             const size_t wbytes = (size_t)9 * nch * Nt * 16;
-            size_t tot = wbytes + halo + (size_t)(Nt + 8) * 4 + 256;
+            size_t tot = wbytes + halo + (size_t)(Nt + 8) * 4 + 1024 + 320;      // + PixelNorm partials + barriers
             if (tot <= budget) {
-                while (stages < kMaxStages && tot + (size_t)nch * kHaloPitch * 16 <= budget) { ++stages; tot += (size_t)nch * kHaloPitch * 16; }
+                const size_t stage_b = (size_t)nch * kHaloPitch * 16;
+                int cols_ = 32; while (cols_ < 2 * Nt) cols_ <<= 1;
+                // two CTAs per SM hide the latency of the (few, specialised) warps: take that shape when >= 4 halo slots
+                // still fit in half of the shared memory and the TMEM columns of both fit
+                // Several CTAs per SM hide the latency of the (few, specialised) warps.  Registers (72/thread) allow
+                // 3 CTAs of 9 warps (4 epilogue warps) or 2 CTAs of 13 warps (8 epilogue warps); shared memory must hold
+                // >= 4 halo slots per CTA and the TMEM columns of all resident CTAs must fit in 512.
+                static const int force_occ = getenv("MG_CONV_OCC") ? atoi(getenv("MG_CONV_OCC")) : 0;
+                const size_t base = tot - halo;
+                pl.occupancy = 1; pl.epi_warps = 8;
+                size_t cap = budget;
+                if ((force_occ == 0 || force_occ == 3) && cols_ <= 128 && base + 4 * stage_b <= 73 * 1024) { pl.occupancy = 3; pl.epi_warps = 4; cap = 73 * 1024; }
+                else if ((force_occ == 0 || force_occ >= 2) && cols_ <= 256 && base + 4 * stage_b <= 110 * 1024) { pl.occupancy = 2; cap = 110 * 1024; }
+                if (pl.occupancy > 1) { tot = base + 4 * stage_b; stages = 4; }
+                while (stages < kMaxStages && tot + stage_b <= cap) { ++stages; tot += stage_b; }
                 pl.Nt = Nt; pl.stages = stages; pl.smem = tot;
                 pl.n_slices = (Cout + Nt - 1) / Nt;
                 int cols = 32; while (cols < 2 * Nt) cols <<= 1;
@@ -323,15 +398,21 @@ int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* 
     p.B = B; p.H = H; p.W = W; p.Hin = ups ? H / 2 : H; p.Win = ups ? W / 2 : W; p.Cin = Cin; p.Cout = Cout;
     p.upsample = ups; p.lrelu = flags & 1; p.pixelnorm = pn;
     p.tiles_x = (W + kTileW - 1) / kTileW; p.tiles_y = (H + kTileH - 1) / kTileH; p.n_tiles = B * p.tiles_x * p.tiles_y;
-    p.Nt = pl.Nt; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
+    p.Nt = pl.Nt; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols; p.epi_warps = pl.epi_warps;
     p.idiv = make_item_div(Cin / 8);
+    p.consumer_fence = getenv("MG_CONSUMER_FENCE") ? 1 : 0;
+    p.tiles_per_img = p.tiles_x * p.tiles_y;
+    p.div_img = make_fast_div(p.tiles_per_img);
+    p.div_tx = make_fast_div(p.tiles_x);
+    if (p.n_tiles >= (1 << 20)) return MG_ERR_UNSUPPORTED;
     static int sm_count = 0;
     if (!sm_count) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
     cudaFuncSetAttribute(k_conv3x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-    const int per_slice = max(1, min(p.n_tiles, sm_count / pl.n_slices > 0 ? sm_count / pl.n_slices : 1));
+    const int ctas = sm_count * pl.occupancy;
+    const int per_slice = max(1, min(p.n_tiles, ctas / pl.n_slices > 0 ? ctas / pl.n_slices : 1));
     {
         ProfScope ps(dgrad ? "k_conv3x3_dgrad" : "k_conv3x3_fprop", st);
-        k_conv3x3<<<dim3(per_slice, pl.n_slices), kConvThreads, pl.smem, st>>>(p);
+        k_conv3x3<<<dim3(per_slice, pl.n_slices), (pl.epi_warps + 5) * 32, pl.smem, st>>>(p);
     }
     return check_launch("k_conv3x3");
 }

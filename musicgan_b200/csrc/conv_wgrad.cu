@@ -14,12 +14,14 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include "conv_common.cuh"
+#include <cstdlib>
 
 namespace mg {
 using namespace umma;
 
 constexpr int kDyPitch = 130;          // pixels per channel chunk of the staged dy tile (128 + 2: bank spread)
-constexpr int kWgradThreads = 288;
+constexpr int kWgradMmaWarps = 3;       // taps are dealt round-robin to three MMA-issuing warps (72 MMAs per tile)
+constexpr int kWgradThreads = (8 + kWgradMmaWarps) * 32;
 
 struct WgradParams {
     const __nv_bfloat16* dy;    // [B][H][W][Cout]
@@ -27,8 +29,12 @@ struct WgradParams {
     float* dw;                  // [Cout][Cin][3][3], accumulated atomically
     int B, H, W, Hin, Win, Cin, Cout, upsample;
     int tiles_x, tiles_y, n_tiles;
-    int taps_per_group, tmem_cols, stages;
+    int taps_per_group, tmem_cols, stages, dy_chunks;
     ItemDiv idiv_x, idiv_dy;
+    unsigned bar_offset;
+    int tiles_per_img;
+    FastDiv div_img, div_tx;
+    int consumer_fence;
 };
 
 __global__ void __launch_bounds__(kWgradThreads, 1)
@@ -42,20 +48,21 @@ k_conv3x3_wgrad(const WgradParams p) {
     const int co_n = min(128, p.Cout - co0);
     const int nch_dy = co_n >> 3;
 
-    // per stage: dy region (16 chunks reserved so that the unused M rows still address this CTA's smem) + x halo
-    const size_t dy_bytes = (size_t)16 * kDyPitch * 16;
+    // per stage: dy tile (only the real channel chunks; the MMA's unused M rows read whatever follows in this CTA's
+    // shared memory -- the host pads the allocation so that those reads stay inside it) + x halo
+    const size_t dy_bytes = (size_t)p.dy_chunks * kDyPitch * 16;
     const size_t x_bytes = (size_t)nch_x * kHaloPitch * 16;
     const size_t stage_bytes = dy_bytes + x_bytes;
     unsigned char* stage0 = smem;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_offset);
     uint64_t* full = bars;                    // [kMaxStages]
     uint64_t* empty = bars + kMaxStages;      // [kMaxStages]
     uint64_t* done = bars + 2 * kMaxStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
 
     if (tid == 0) {
-        for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
-        mbar_init(done, 1);
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], kWgradMmaWarps); }
+        mbar_init(done, kWgradMmaWarps);
         mbar_fence_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -74,9 +81,10 @@ k_conv3x3_wgrad(const WgradParams p) {
             const int slot = it % p.stages;
             const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
             mbar_wait(&empty[slot], ph ^ 1u);
-            const int b = tile / tiles_per_img;
-            const int tr = tile - b * tiles_per_img;
-            const int oy0 = (tr / p.tiles_x) * kTileH, ox0 = (tr % p.tiles_x) * kTileW;
+            const int b = fast_div(tile, p.div_img);
+            const int tr = tile - b * p.tiles_per_img;
+            const int tyi = fast_div(tr, p.div_tx);
+            const int oy0 = tyi * kTileH, ox0 = (tr - tyi * p.tiles_x) * kTileW;
             const uint32_t s_dy = smem_u32(stage0 + slot * stage_bytes);
             const uint32_t s_x = s_dy + (uint32_t)dy_bytes;
             // dy tile: 128 pixels x nch_dy chunks (zero outside the image: those pixels must not contribute)
@@ -103,32 +111,38 @@ k_conv3x3_wgrad(const WgradParams p) {
             }
             cp_async_arrive(&full[slot]);
         }
-    } else if (warp == 8) {
-        // ================= MMA issue =================
+    } else if (warp >= 8) {
+        // ================= MMA issue: warp 8 + w issues taps w, w + 3, w + 6 =================
+        const int mw = warp - 8;
         const uint32_t idesc = instr_desc_bf16(p.Cin, true, true);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-            const int slot = it % p.stages;
-            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        // descriptors differ only in the start-address field (16-byte units): formed by integer additions
+        const uint64_t a_desc0 = smem_desc(smem_u32(stage0), 128u, kDyPitch * 16u);
+        const uint64_t b_desc0 = smem_desc(smem_u32(stage0) + (uint32_t)dy_bytes, kHaloW * 16u, kHaloPitch * 16u);
+        const uint32_t stage_units = (uint32_t)(stage_bytes >> 4);
+        int slot = 0; uint32_t ph = 0, accum = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             mbar_wait(&full[slot], ph);
-            fence_proxy_async();
+            if (p.consumer_fence) fence_proxy_async();
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t a0 = smem_u32(stage0 + slot * stage_bytes);
-                const uint32_t b0 = a0 + (uint32_t)dy_bytes;
-                for (int tl = 0; tl < ntaps; ++tl) {
+                const uint64_t da0 = a_desc0 + (uint64_t)(slot * stage_units), db0 = b_desc0 + (uint64_t)(slot * stage_units);
+                for (int tl = mw; tl < ntaps; tl += kWgradMmaWarps) {
                     const int tap = tap0 + tl;
                     const int ky = tap / 3, kx = tap - ky * 3;
                     const uint32_t d = tmem_base + tl * p.Cin;
-                    for (int j = 0; j < 8; ++j) {
-                        const uint64_t da = smem_desc(a0 + (uint32_t)(16 * j) * 16u, 128u, kDyPitch * 16u);
-                        const uint64_t db = smem_desc(b0 + (uint32_t)((2 * j + ky) * kHaloW + kx) * 16u, kHaloW * 16u, kHaloPitch * 16u);
-                        mma_bf16(d, da, db, idesc, !(it == 0 && j == 0));
+                    uint64_t da = da0, db = db0 + (uint64_t)(ky * kHaloW + kx);
+                    mma_bf16(d, da, db, idesc, accum);
+#pragma unroll
+                    for (int j = 1; j < 8; ++j) {
+                        da += 16; db += 2 * kHaloW;
+                        mma_bf16(d, da, db, idesc, 1u);
                     }
                 }
                 mma_commit(&empty[slot]);
             }
+            accum = 1;
             __syncwarp();
+            if (++slot == p.stages) { slot = 0; ph ^= 1u; }
         }
         if (lane == 0) mma_commit(done);
         __syncwarp();
@@ -178,13 +192,27 @@ extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, f
     int cols = 32; while (cols < p.taps_per_group * Cin) cols <<= 1;
     p.tmem_cols = cols;
     const int mblocks = (Cout + 127) / 128;
-    const size_t stage_bytes = (size_t)16 * kDyPitch * 16 + (size_t)(Cin / 8) * kHaloPitch * 16;
-    int stages = (int)((200 * 1024) / stage_bytes);
-    stages = stages > kMaxStages ? kMaxStages : stages;
+    const int mblocks_ = (Cout + 127) / 128;
+    p.dy_chunks = (mblocks_ > 1 ? 128 : Cout) / 8;          // chunks of the widest M block
+    const size_t stage_bytes = (size_t)p.dy_chunks * kDyPitch * 16 + (size_t)(Cin / 8) * kHaloPitch * 16;
+    const size_t reach = (size_t)16 * kDyPitch * 16;        // bytes an M = 128 operand spans from a dy region's start
+    int stages = kMaxStages;
+    size_t smem = 0;
+    for (; stages >= 1; --stages) {
+        const size_t data = (size_t)stages * stage_bytes;
+        const size_t last_dy = (size_t)(stages - 1) * stage_bytes;
+        const size_t need = (last_dy + reach > data ? last_dy + reach : data);
+        smem = align_up(need, 16) + 256;
+        if (smem <= 200 * 1024) { p.bar_offset = (unsigned)align_up(need, 16); break; }
+    }
     if (stages < 1) return MG_ERR_UNSUPPORTED;
     p.stages = stages;
     p.idiv_x = make_item_div(Cin / 8);
-    const size_t smem = stages * stage_bytes + 256;
+    p.consumer_fence = getenv("MG_CONSUMER_FENCE") ? 1 : 0;
+    p.tiles_per_img = p.tiles_x * p.tiles_y;
+    p.div_img = make_fast_div(p.tiles_per_img);
+    p.div_tx = make_fast_div(p.tiles_x);
+    if (p.n_tiles >= (1 << 20)) return MG_ERR_UNSUPPORTED;
     static int sm_count = 0;
     if (!sm_count) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
     cudaFuncSetAttribute(k_conv3x3_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -50,7 +50,7 @@ k_debug_umma(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restric
                 da = smem_desc(a0 + (kk * 16) * 16, 128, pA * 16);
                 db = smem_desc(b0 + (kk * 16) * 16, 128, pB * 16);
             }
-            mma_bf16(tm, da, db, idesc, kk > 0);
+            mma_bf16(tm, da, db, idesc, kk > 0 ? 1u : 0u);
         }
         mma_commit(&bar);
     }

@@ -1,0 +1,93 @@
+"""CUDA-graph capture of the two optimisation steps (reference train.py:143-175 and :191-214).
+
+At the final resolutions one WGAN-GP iteration is ~250 tensor-core launches plus the pointwise kernels and the
+optimiser: issued from Python it is host bound.  The critic step and the generator step are therefore captured
+ONCE each (after a warm-up on a side stream) and replayed; all launches of libmusicgan_b200.so go to torch's current
+stream, so they are captured like any ATen kernel.  Packed-weight caches are invalidated before capture so that the
+weight re-pack kernels are part of the graph (weights change between replays).
+
+`alpha` is baked into the graphs: re-capture when it changes (bench: constant; `train` uses the eager steps while
+alpha ramps and may switch to graphs once alpha == 1).
+"""
+from __future__ import annotations
+
+import torch as th
+
+from . import networks
+from .networks import ops
+
+
+class GraphedSteps:
+    def __init__(self, gen, disc, optim_gen, optim_disc, batch: int, rand_channels: int, resolution: int, alpha: float,
+                 grad_sync_d=None, grad_sync_g=None, warmup: int = 3):
+        self.gen, self.disc, self.og, self.od = gen, disc, optim_gen, optim_disc
+        self.batch, self.alpha = batch, alpha
+        self.sync_d, self.sync_g = grad_sync_d, grad_sync_g
+        dev = next(gen.parameters()).device
+        self.x_real = th.zeros(batch, 2, resolution, resolution, device=dev)
+        self.z_shape = (batch, rand_channels, 2, 2)
+        self.d_stats = self.g_stats = None
+        self._gd = self._gg = None
+        self._capture(warmup)
+
+    # -- the two step bodies (static shapes, no host sync) -------------------------------------------------
+    def _critic_body(self):
+        gen, disc, alpha, n = self.gen, self.disc, self.alpha, self.batch
+        z = th.randn(self.z_shape, device=self.x_real.device)
+        with th.no_grad():
+            x_fake = gen(z, alpha)
+        out = disc(th.cat([self.x_real, x_fake], dim=0), alpha)
+        d_loss = networks.wasserstein_discriminator_loss(out[:n], out[n:])
+        gp = disc.gradient_penalty(self.x_real, x_fake, alpha)
+        params = [p for p in disc.parameters()]
+        grads = th.autograd.grad(d_loss + gp, params, allow_unused=True)
+        for p, g in zip(params, grads):
+            p.grad = g
+        if self.sync_d is not None:
+            self.sync_d()
+        self.od.step()
+        return th.stack([d_loss.detach(), gp.detach(), out[:n].mean().detach(), out[n:].mean().detach()])
+
+    def _generator_body(self):
+        gen, disc, alpha = self.gen, self.disc, self.alpha
+        z = th.randn(self.z_shape, device=self.x_real.device)
+        out_fake = disc(gen(z, alpha), alpha)
+        g_loss = networks.wasserstein_generator_loss(out_fake)
+        # only G's gradients are needed (the reference computes and discards D's, train.py:208-214)
+        params = [p for p in gen.parameters()]
+        grads = th.autograd.grad(g_loss, params, allow_unused=True)
+        for p, g in zip(params, grads):
+            p.grad = g
+        if self.sync_g is not None:
+            self.sync_g()
+        self.og.step()
+        return th.stack([g_loss.detach(), out_fake.mean().detach()])
+
+    def _capture(self, warmup: int):
+        side = th.cuda.Stream()
+        side.wait_stream(th.cuda.current_stream())
+        with th.cuda.stream(side):
+            for _ in range(warmup):
+                self._critic_body()
+                self._generator_body()
+        th.cuda.current_stream().wait_stream(side)
+        th.cuda.synchronize()
+        ops.invalidate_pack_cache()
+        self._gd = th.cuda.CUDAGraph()
+        with th.cuda.graph(self._gd):
+            self.d_stats = self._critic_body()
+        ops.invalidate_pack_cache()
+        self._gg = th.cuda.CUDAGraph()
+        with th.cuda.graph(self._gg, pool=self._gd.pool()):
+            self.g_stats = self._generator_body()
+        ops.invalidate_pack_cache()
+
+    # -- replay ---------------------------------------------------------------------------------------------
+    def critic_step(self, x_real: th.Tensor) -> th.Tensor:
+        self.x_real.copy_(x_real, non_blocking=True)
+        self._gd.replay()
+        return self.d_stats          # [d_loss, grad_pen, mean D(real), mean D(fake)] (device tensor, overwritten on replay)
+
+    def generator_step(self) -> th.Tensor:
+        self._gg.replay()
+        return self.g_stats          # [g_loss, mean D(fake)]

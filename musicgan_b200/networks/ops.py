@@ -51,6 +51,14 @@ def _workspace(dev, nbytes: int) -> th.Tensor:
     return ws
 
 
+_pack_epoch = [0]
+
+
+def invalidate_pack_cache() -> None:
+    """Forget every cached packed weight (used around CUDA-graph capture so that the pack kernels are captured)."""
+    _pack_epoch[0] += 1
+
+
 def _packed_weights(w: th.Tensor, cin: int, cout: int, dgrad: bool):
     """Packed bf16 copy of a weight tensor, cached ON the parameter object per (version, storage address): parameters
     change once per optimiser step but are read by several forward / backward kernels.  The cache lives and dies with
@@ -62,7 +70,7 @@ def _packed_weights(w: th.Tensor, cin: int, cout: int, dgrad: bool):
     if cache is None:
         cache = {}
         w._mg_packed = cache
-    stamp = (w._version, w.data_ptr())
+    stamp = (w._version, w.data_ptr(), _pack_epoch[0])
     hit = cache.get(dgrad)
     if hit is not None and hit[0] == stamp:
         return hit[1]
