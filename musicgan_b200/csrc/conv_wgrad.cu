@@ -19,9 +19,10 @@
 namespace mg {
 using namespace umma;
 
-constexpr int kDyPitch = 130;          // pixels per channel chunk of the staged dy tile (128 + 2: bank spread)
-constexpr int kWgradMmaWarps = 3;       // taps are dealt round-robin to three MMA-issuing warps (72 MMAs per tile)
-constexpr int kWgradThreads = (8 + kWgradMmaWarps) * 32;
+constexpr int kDyPitch = 129;          // pixels per channel chunk of the staged dy tile (odd: spreads the transposer's banks)
+constexpr int kWgradMmaWarps = 3;      // taps are dealt round-robin to three MMA-issuing warps (72 MMAs per tile)
+constexpr int kXposeWarps = 8;         // dy tile: smem -> registers -> TMEM (A operand), two warps per TMEM lane quarter
+constexpr int kWgradThreads = (kXposeWarps + 4 + kWgradMmaWarps) * 32;     // 480
 
 struct WgradParams {
     const __nv_bfloat16* dy;    // [B][H][W][Cout]
@@ -30,13 +31,18 @@ struct WgradParams {
     int B, H, W, Hin, Win, Cin, Cout, upsample;
     int tiles_x, tiles_y, n_tiles;
     int taps_per_group, tmem_cols, stages, dy_chunks;
-    ItemDiv idiv_x, idiv_dy;
+    ItemDiv idiv_x;
     unsigned bar_offset;
     int tiles_per_img;
     FastDiv div_img, div_tx;
-    int consumer_fence;
 };
 
+// Why the A operand lives in TMEM: with both operands in shared memory every one of the 72 MMAs of a tile re-reads the
+// 128-row (mostly padding) dy operand, 4 KB each -> ~290 KB of shared-memory reads per tile, which bounds the kernel
+// at ~2500 cycles/tile.  Here the dy tile is transposed ONCE per tile into TMEM (lane = output channel, column = pixel
+// pair) and all nine taps read it from there; shared memory only serves the small shifted x windows.
+// Output channel co sits on TMEM lane (co & 3) * 32 + (co >> 2) so that the four lane quarters (and therefore the
+// transposer warps) share the work evenly even when Cout is small.
 __global__ void __launch_bounds__(kWgradThreads, 1)
 k_conv3x3_wgrad(const WgradParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -48,38 +54,38 @@ k_conv3x3_wgrad(const WgradParams p) {
     const int co_n = min(128, p.Cout - co0);
     const int nch_dy = co_n >> 3;
 
-    // per stage: dy tile (only the real channel chunks; the MMA's unused M rows read whatever follows in this CTA's
-    // shared memory -- the host pads the allocation so that those reads stay inside it) + x halo
     const size_t dy_bytes = (size_t)p.dy_chunks * kDyPitch * 16;
     const size_t x_bytes = (size_t)nch_x * kHaloPitch * 16;
     const size_t stage_bytes = dy_bytes + x_bytes;
     unsigned char* stage0 = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_offset);
-    uint64_t* full = bars;                    // [kMaxStages]
-    uint64_t* empty = bars + kMaxStages;      // [kMaxStages]
-    uint64_t* done = bars + 2 * kMaxStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+    uint64_t* full = bars;                    // [kMaxStages]  producers -> transposers + MMA
+    uint64_t* empty = bars + kMaxStages;      // [kMaxStages]  MMA commit -> producers
+    uint64_t* a_full = bars + 2 * kMaxStages; // [2]           transposers -> MMA
+    uint64_t* a_empty = a_full + 2;           // [2]           MMA commit -> transposers
+    uint64_t* done = a_full + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 5);
 
+    constexpr int kProd0 = kXposeWarps, kMma0 = kXposeWarps + 4;
     if (tid == 0) {
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], kWgradMmaWarps); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], kXposeWarps * 32); mbar_init(&a_empty[i], kWgradMmaWarps); }
         mbar_init(done, kWgradMmaWarps);
         mbar_fence_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, p.tmem_cols);
+    if (warp == kMma0) tmem_alloc(tmem_slot, p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const uint32_t tmem_a = tmem_base + (uint32_t)(p.tmem_cols - 128);      // two A buffers of 64 columns
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= kProd0 && warp < kMma0) {
         // ================= producers =================
-        const int pt = tid - 128;
+        const int pt = tid - kProd0 * 32;
         const unsigned dy_magic = ((1u << 20) + nch_dy - 1) / nch_dy;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-            const int slot = it % p.stages;
-            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        int slot = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             mbar_wait(&empty[slot], ph ^ 1u);
             const int b = fast_div(tile, p.div_img);
             const int tr = tile - b * p.tiles_per_img;
@@ -104,72 +110,107 @@ k_conv3x3_wgrad(const WgradParams p) {
                 const int pos = (int)(((unsigned)i * p.idiv_x.magic) >> 20), c = i - pos * nch_x;
                 const int hy = (pos * 6554) >> 16, hx = pos - hy * kHaloW;
                 const int iy = oy0 - 1 + hy, ix = ox0 - 1 + hx;
-                const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                const bool ok = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
                 const int sy = p.upsample ? (iy >> 1) : iy, sx = p.upsample ? (ix >> 1) : ix;
                 const void* src = ok ? (const void*)(reinterpret_cast<const uint4*>(xb + ((size_t)sy * p.Win + sx) * p.Cin) + c) : (const void*)p.x;
                 cp_async16(s_x + (uint32_t)(c * kHaloPitch + pos) * 16u, src, ok ? 16u : 0u);
             }
             cp_async_arrive(&full[slot]);
+            if (++slot == p.stages) { slot = 0; ph ^= 1u; }
         }
-    } else if (warp >= 8) {
-        // ================= MMA issue: warp 8 + w issues taps w, w + 3, w + 6 =================
-        const int mw = warp - 8;
-        const uint32_t idesc = instr_desc_bf16(p.Cin, true, true);
-        // descriptors differ only in the start-address field (16-byte units): formed by integer additions
-        const uint64_t a_desc0 = smem_desc(smem_u32(stage0), 128u, kDyPitch * 16u);
+    } else if (warp >= kMma0) {
+        // ================= MMA issue: warp kMma0 + w issues taps w, w + 3, w + 6 (A from TMEM, B from smem) =================
+        const int mw = warp - kMma0;
+        const uint32_t idesc = instr_desc_bf16(p.Cin, false, true);
         const uint64_t b_desc0 = smem_desc(smem_u32(stage0) + (uint32_t)dy_bytes, kHaloW * 16u, kHaloPitch * 16u);
         const uint32_t stage_units = (uint32_t)(stage_bytes >> 4);
-        int slot = 0; uint32_t ph = 0, accum = 0;
+        int slot = 0, buf = 0; uint32_t ph = 0, aph = 0, accum = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             mbar_wait(&full[slot], ph);
-            if (p.consumer_fence) fence_proxy_async();
+            mbar_wait(&a_full[buf], aph);
             tc_fence_after();
             if (lane == 0) {
-                const uint64_t da0 = a_desc0 + (uint64_t)(slot * stage_units), db0 = b_desc0 + (uint64_t)(slot * stage_units);
+                const uint64_t db0 = b_desc0 + (uint64_t)(slot * stage_units);
+                const uint32_t a0 = tmem_a + buf * 64;
                 for (int tl = mw; tl < ntaps; tl += kWgradMmaWarps) {
                     const int tap = tap0 + tl;
                     const int ky = tap / 3, kx = tap - ky * 3;
                     const uint32_t d = tmem_base + tl * p.Cin;
-                    uint64_t da = da0, db = db0 + (uint64_t)(ky * kHaloW + kx);
-                    mma_bf16(d, da, db, idesc, accum);
+                    uint64_t db = db0 + (uint64_t)(ky * kHaloW + kx);
+                    mma_bf16_ts(d, a0, db, idesc, accum);
 #pragma unroll
                     for (int j = 1; j < 8; ++j) {
-                        da += 16; db += 2 * kHaloW;
-                        mma_bf16(d, da, db, idesc, 1u);
+                        db += 2 * kHaloW;
+                        mma_bf16_ts(d, a0 + j * 8, db, idesc, 1u);
                     }
                 }
                 mma_commit(&empty[slot]);
+                mma_commit(&a_empty[buf]);
             }
             accum = 1;
             __syncwarp();
             if (++slot == p.stages) { slot = 0; ph ^= 1u; }
+            if (++buf == 2) { buf = 0; aph ^= 1u; }
         }
         if (lane == 0) mma_commit(done);
         __syncwarp();
     } else {
-        // ================= epilogue: one flush of the TMEM accumulators =================
-        const bool any = blockIdx.x < p.n_tiles;
-        mbar_wait(done, 0);
-        tc_fence_after();
-        const int m = tid;      // TMEM lane == local output channel
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int tl = 0; tl < ntaps; ++tl) {
-            const int tap = tap0 + tl;
-            for (int c0 = 0; c0 < p.Cin; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + tl * p.Cin + c0, v);
-                tmem_wait_ld();
-                if (any && m < co_n) {
-                    float* dst = p.dw + ((size_t)(co0 + m) * p.Cin + c0) * 9 + tap;
+        // ================= transposers: dy tile smem -> TMEM A operand; then (warps 0-3) the final flush =================
+        const int quarter = warp & 3, khalf = warp >> 2;
+        const int co = 4 * lane + quarter;                  // local output channel owned by this TMEM lane
+        const bool row_ok = co < co_n;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        int slot = 0, buf = 0; uint32_t ph = 0, aph = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            mbar_wait(&a_empty[buf], aph ^ 1u);
+            mbar_wait(&full[slot], ph);
+            tc_fence_after();
+            const unsigned char* s_dy = stage0 + slot * stage_bytes;
+            const unsigned char* row = s_dy + ((size_t)(co >> 3) * kDyPitch) * 16 + (co & 7) * 2;
+            const uint32_t ta = tmem_a + buf * 64 + khalf * 32 + lane_addr;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) atomicAdd(dst + j * 9, v[j]);
+            for (int g = 0; g < 4; ++g) {                    // 4 groups of 8 columns = 16 pixels each
+                uint32_t r[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int pix = khalf * 64 + g * 16 + 2 * j;
+                    uint32_t lo = 0, hi = 0;
+                    if (row_ok) {
+                        lo = *reinterpret_cast<const uint16_t*>(row + (size_t)pix * 16);
+                        hi = *reinterpret_cast<const uint16_t*>(row + (size_t)(pix + 1) * 16);
+                    }
+                    r[j] = lo | (hi << 16);
+                }
+                tmem_st8(ta + g * 8, r);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&a_full[buf]);
+            if (++slot == p.stages) { slot = 0; ph ^= 1u; }
+            if (++buf == 2) { buf = 0; aph ^= 1u; }
+        }
+        if (warp < 4) {
+            mbar_wait(done, 0);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + lane_addr;
+            for (int tl = 0; tl < ntaps; ++tl) {
+                const int tap = tap0 + tl;
+                for (int c0 = 0; c0 < p.Cin; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + tl * p.Cin + c0, v);
+                    tmem_wait_ld();
+                    if (row_ok) {
+                        float* dst = p.dw + ((size_t)(co0 + co) * p.Cin + c0) * 9 + tap;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) atomicAdd(dst + j * 9, v[j]);
+                    }
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, p.tmem_cols);
+    if (warp == kMma0) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 }  // namespace mg
@@ -187,28 +228,27 @@ extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, f
     p.B = B; p.H = H; p.W = W; p.Hin = upsample_in ? H / 2 : H; p.Win = upsample_in ? W / 2 : W; p.Cin = Cin; p.Cout = Cout;
     p.upsample = upsample_in ? 1 : 0;
     p.tiles_x = (W + kTileW - 1) / kTileW; p.tiles_y = (H + kTileH - 1) / kTileH; p.n_tiles = B * p.tiles_x * p.tiles_y;
-    p.taps_per_group = 512 / Cin > 9 ? 9 : 512 / Cin;
-    const int groups = (9 + p.taps_per_group - 1) / p.taps_per_group;
-    int cols = 32; while (cols < p.taps_per_group * Cin) cols <<= 1;
+    // Tap groups: a CTA keeps taps_per_group x Cin accumulator columns plus two 64-column A buffers in its 512 TMEM
+    // columns; more taps than fit are split over blockIdx.y (balanced, e.g. 9 -> 5 + 4), each group re-reading the tiles.
+    int tpp = (512 - 128) / Cin; tpp = tpp > 9 ? 9 : (tpp < 1 ? 1 : tpp);
+    const int groups = (9 + tpp - 1) / tpp;
+    p.taps_per_group = (9 + groups - 1) / groups;
+    int cols = 32; while (cols < p.taps_per_group * Cin + 128) cols <<= 1;
     p.tmem_cols = cols;
+    const int occ = 1;
     const int mblocks = (Cout + 127) / 128;
-    const int mblocks_ = (Cout + 127) / 128;
-    p.dy_chunks = (mblocks_ > 1 ? 128 : Cout) / 8;          // chunks of the widest M block
+    p.dy_chunks = (mblocks > 1 ? 128 : Cout) / 8;           // chunks of the widest M block
     const size_t stage_bytes = (size_t)p.dy_chunks * kDyPitch * 16 + (size_t)(Cin / 8) * kHaloPitch * 16;
-    const size_t reach = (size_t)16 * kDyPitch * 16;        // bytes an M = 128 operand spans from a dy region's start
     int stages = kMaxStages;
     size_t smem = 0;
     for (; stages >= 1; --stages) {
-        const size_t data = (size_t)stages * stage_bytes;
-        const size_t last_dy = (size_t)(stages - 1) * stage_bytes;
-        const size_t need = (last_dy + reach > data ? last_dy + reach : data);
+        const size_t need = (size_t)stages * stage_bytes;
         smem = align_up(need, 16) + 256;
         if (smem <= 200 * 1024) { p.bar_offset = (unsigned)align_up(need, 16); break; }
     }
     if (stages < 1) return MG_ERR_UNSUPPORTED;
     p.stages = stages;
     p.idiv_x = make_item_div(Cin / 8);
-    p.consumer_fence = getenv("MG_CONSUMER_FENCE") ? 1 : 0;
     p.tiles_per_img = p.tiles_x * p.tiles_y;
     p.div_img = make_fast_div(p.tiles_per_img);
     p.div_tx = make_fast_div(p.tiles_x);
@@ -216,7 +256,7 @@ extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, f
     static int sm_count = 0;
     if (!sm_count) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
     cudaFuncSetAttribute(k_conv3x3_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int gx = sm_count / (groups * mblocks);
+    int gx = sm_count * occ / (groups * mblocks);
     gx = gx < 1 ? 1 : gx;
     gx = gx > p.n_tiles ? p.n_tiles : gx;
     cudaStream_t st = (cudaStream_t)stream;

@@ -26,23 +26,49 @@ k_debug_umma(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restric
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint4* sA; uint4* sB; int pA, pB;
+    // modes 2 / 3: A [128][K] row major goes to TMEM (thread m = row m, pairs of K packed per 32-bit column; mode 3 swaps
+    // the halves of each pair), B [K][N] MN-major in smem as in mode 1
     if (mode == 0) { pA = Ra + 1; pB = N + 1; } else { pA = K + 1; pB = K + 1; }
     sA = reinterpret_cast<uint4*>(smem);
     sB = sA + (mode == 0 ? (K / 8) * pA : (128 / 8) * pA);
     if (mode == 0) { stage_chunks(A, Ra, K, sA, pA); stage_chunks(B, N, K, sB, pB); }
-    else           { stage_chunks(A, K, 128, sA, pA); stage_chunks(B, K, N, sB, pB); }
-    if (warp == 0) tmem_alloc(&tmem_base, 256);
+    else if (mode == 1) { stage_chunks(A, K, 128, sA, pA); stage_chunks(B, K, N, sB, pB); }
+    else stage_chunks(B, K, N, sB, pB);
+    if (warp == 0) tmem_alloc(&tmem_base, 512);
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tm = tmem_base;
+    const uint32_t tm_a = tm + 256;           // A operand columns (modes 2 / 3) after the accumulator
+    if (mode >= 2) {
+        const int m = tid;
+        for (int k0 = 0; k0 < K; k0 += 16) {
+            uint32_t r[8];
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t lo = *reinterpret_cast<const uint16_t*>(A + (size_t)m * K + k0 + 2 * j);
+                const uint32_t hi = *reinterpret_cast<const uint16_t*>(A + (size_t)m * K + k0 + 2 * j + 1);
+                r[j] = mode == 2 ? (lo | (hi << 16)) : (hi | (lo << 16));
+            }
+            tmem_st8(tm_a + ((uint32_t)(warp * 32) << 16) + (k0 >> 1), r);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
     if (tid == 0) {
         const uint32_t idesc = instr_desc_bf16(N, mode == 1, mode == 1);
+        (void)idesc;
         const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
         for (int kk = 0; kk < K / 16; ++kk) {
             uint64_t da, db;
+            if (mode >= 2) {
+                db = smem_desc(b0 + (kk * 16) * 16, 128, pB * 16);
+                mma_bf16_ts(tm, tm_a + kk * 8, db, instr_desc_bf16(N, false, true), kk > 0 ? 1u : 0u);
+                continue;
+            }
             if (mode == 0) {
                 da = smem_desc(a0 + (row_off + kk * 2 * pA) * 16, pA * 16, grp_rows * 16);
                 db = smem_desc(b0 + (kk * 2 * pB) * 16, pB * 16, 128);
@@ -65,7 +91,7 @@ k_debug_umma(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restric
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tm, 256);
+    if (warp == 0) tmem_dealloc(tm, 512);
 }
 }  // namespace mg
 

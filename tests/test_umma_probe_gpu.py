@@ -18,10 +18,14 @@ def _run(K, N, mode, Ra=128, row_off=0, grp_rows=8, seed=0):
         B = torch.randn(N, K, generator=g).bfloat16().cuda()
         rows = torch.tensor([row_off + (m // 8) * grp_rows + m % 8 for m in range(128)])
         ref = A.float()[rows.cuda()] @ B.float().t()
-    else:
+    elif mode == 1:
         A = torch.randn(K, 128, generator=g).bfloat16().cuda()
         B = torch.randn(K, N, generator=g).bfloat16().cuda()
         ref = A.float().t() @ B.float()
+    else:
+        A = torch.randn(128, K, generator=g).bfloat16().cuda()
+        B = torch.randn(K, N, generator=g).bfloat16().cuda()
+        ref = A.float() @ B.float()
     D = torch.zeros(128, N, device="cuda")
     _lib.check(l.mg_debug_umma_gemm(A.data_ptr(), B.data_ptr(), D.data_ptr(), K, N, mode, Ra, row_off, grp_rows,
                                     torch.cuda.current_stream().cuda_stream), "mg_debug_umma_gemm")
@@ -48,3 +52,12 @@ def test_k_major_shifted_rows(row_off, grp_rows):
 def test_mn_major(K, N):
     err, scale = _run(K, N, 1)
     assert err <= 2e-3 * scale, (err, scale)
+
+
+@pytest.mark.parametrize("K,N", [(16, 16), (128, 32), (128, 144)])
+def test_a_operand_from_tmem(K, N):
+    """A rows in TMEM (lane = row, two bf16 per 32-bit column, low half = even k), B MN-major in smem."""
+    err, scale = _run(K, N, 2)
+    err_swapped, _ = _run(K, N, 3)
+    print(f"TS mode K={K} N={N}: err {err:.3e} (swapped halves {err_swapped:.3e}), scale {scale:.3e}")
+    assert err <= 2e-3 * scale, (err, err_swapped, scale)
