@@ -94,10 +94,12 @@ k_conv3x3(const ConvParams p) {
         {   // resident weights of this slice + bias
             const uint4* src = p.wpack + (size_t)9 * nch * n0;
             const int total = 9 * nch * nt;
-            for (int i = pt; i < total; i += 128) sW[i] = __ldg(src + i);
+            // all chunks in flight at once (the deep layers carry up to 140 KB of weights per slice: a synchronous
+            // load loop here used to dominate the run time of the small-spatial layers)
+            const uint32_t sw_addr = smem_u32(sW);
+            for (int i = pt; i < total; i += 128) cp_async16(sw_addr + (uint32_t)i * 16u, src + i, 16u);
             for (int i = pt; i < nt; i += 128) sBias[i] = p.bias ? p.bias[n0 + i] : 0.0f;
-            fence_proxy_async();
-            mbar_arrive(w_full);
+            cp_async_arrive(w_full);
         }
         const int items = kHaloPos * nch;
         // Per-thread item table, built once: for each 16-byte chunk this thread copies per tile, where it comes from

@@ -189,11 +189,12 @@ k_conv3x3_wgrad(const WgradParams p) {
             if (++slot == p.stages) { slot = 0; ph ^= 1u; }
             if (++buf == 2) { buf = 0; aph ^= 1u; }
         }
-        if (warp < 4) {
+        {   // final flush: the two warps of a lane quarter split the taps; plain stores when no other CTA contributes
             mbar_wait(done, 0);
             tc_fence_after();
             const uint32_t taddr = tmem_base + lane_addr;
-            for (int tl = 0; tl < ntaps; ++tl) {
+            const bool exclusive = gridDim.x == 1;
+            for (int tl = khalf; tl < ntaps; tl += 2) {
                 const int tap = tap0 + tl;
                 for (int c0 = 0; c0 < p.Cin; c0 += 16) {
                     float v[16];
@@ -201,8 +202,13 @@ k_conv3x3_wgrad(const WgradParams p) {
                     tmem_wait_ld();
                     if (row_ok) {
                         float* dst = p.dw + ((size_t)(co0 + co) * p.Cin + c0) * 9 + tap;
+                        if (exclusive) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) atomicAdd(dst + j * 9, v[j]);
+                            for (int j = 0; j < 16; ++j) dst[j * 9] = v[j];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) atomicAdd(dst + j * 9, v[j]);
+                        }
                     }
                 }
             }
@@ -231,8 +237,16 @@ extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, f
     // Tap groups: a CTA keeps taps_per_group x Cin accumulator columns plus two 64-column A buffers in its 512 TMEM
     // columns; more taps than fit are split over blockIdx.y (balanced, e.g. 9 -> 5 + 4), each group re-reading the tiles.
     int tpp = (512 - 128) / Cin; tpp = tpp > 9 ? 9 : (tpp < 1 ? 1 : tpp);
-    const int groups = (9 + tpp - 1) / tpp;
+    int groups = (9 + tpp - 1) / tpp;
+    static int sm_count_ = 0;
+    if (!sm_count_) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev); }
+    {   // small-spatial layers: too few tiles to fill the GPU -> spread the taps over more CTAs instead (fewer columns to
+        // flush per CTA, and with one CTA per group no atomics at all)
+        const int mb = (Cout + 127) / 128;
+        while (groups < 9 && p.n_tiles * groups * mb < sm_count_) groups = groups < 3 ? 3 : 9;
+    }
     p.taps_per_group = (9 + groups - 1) / groups;
+    groups = (9 + p.taps_per_group - 1) / p.taps_per_group;
     int cols = 32; while (cols < p.taps_per_group * Cin + 128) cols <<= 1;
     p.tmem_cols = cols;
     const int occ = 1;
