@@ -150,7 +150,8 @@ int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, float* dbias
  *                      (ToMagnPhaseLayer, networks/generator.py:43-52, and rgb_expand's data gradient)
  * mg_rgb_wgrad_bf16    gw[c][k] += sum_p (g*mask)[p][c] x[k][p], gb[c] += sum_p (g*mask)[p][c]  (fp32, caller zeroes)
  * mg_pool2_bf16        AvgPool2d(2,2) on bf16 NHWC (networks/discriminator.py:24,131); adjoint != 0 runs its
- *                      transpose (each input pixel * 0.25 replicated to a 2x2 block); Ho, Wo = the SMALLER dims
+ *                      transpose (each input pixel * 0.25 replicated to a 2x2 block); adjoint == 2: 2x2 SUM pooling (backward of
+ *                      the nearest x2 upsampling, generator.py:26-29); Ho, Wo = the SMALLER dims
  * ---------------------------------------------------------------------------------------- */
 int mg_rgb_expand_bf16(const float* x, const float* w, const float* b, const void* mask_src, void* y,
                        int B, int64_t HW, int C, int mode, mgStream stream);
@@ -160,6 +161,11 @@ int mg_rgb_wgrad_bf16(const void* g, const void* mask_src, const float* x, float
 int mg_pool2_bf16(const void* in, void* out, int B, int Ho, int Wo, int C, int adjoint, mgStream stream);
 /* LeakyReLU(0.2) backward fused with the bias gradient: gz = gy * mask(y) (bf16 NHWC), gb[c] += sum over pixels of gz
  * (fp32, caller zeroes, may be NULL).  (backward of the Conv2d + LeakyReLU pairs, discriminator.py:15-22,26-33) */
+/* PixelNorm + LeakyReLU backward of a generator half-block (layers.py:11-17 after generator.py:23,38):
+ * go, o [n_pixels][C] bf16 (o = the normalised forward output), inv_norm [n_pixels] fp32 (from mg_conv3x3_bf16 flag 2)
+ * -> gz [n_pixels][C] bf16 = gradient w.r.t. the convolution output (+bias), gb[c] += sum over pixels (may be NULL). */
+int mg_pixelnorm_lrelu_bwd_bf16(const void* go, const void* o, const float* inv_norm, void* gz, float* gb,
+                                int64_t n_pixels, int C, mgStream stream);
 int mg_lrelu_bwd_bf16(const void* gy, const void* y, void* gz, float* gb, int64_t n_pixels, int C, mgStream stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -138,7 +138,7 @@ k_rgb_wgrad(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict
 
 // ---- 2x2 average pooling, bf16 NHWC ---------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_pool2(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int Ho, int Wo, int C8, int64_t total) {
+k_pool2(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int Ho, int Wo, int C8, int64_t total, float scale) {
     // one thread = 8 channels of one output pixel
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C8);
@@ -154,7 +154,7 @@ k_pool2(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, i
         for (int j = 0; j < 4; ++j) {
             const float2 a = __bfloat1622float2(v00.h[j]), bb = __bfloat1622float2(v01.h[j]);
             const float2 cc = __bfloat1622float2(v10.h[j]), d = __bfloat1622float2(v11.h[j]);
-            o.h[j] = __floats2bfloat162_rn(0.25f * ((a.x + bb.x) + (cc.x + d.x)), 0.25f * ((a.y + bb.y) + (cc.y + d.y)));
+            o.h[j] = __floats2bfloat162_rn(scale * ((a.x + bb.x) + (cc.x + d.x)), scale * ((a.y + bb.y) + (cc.y + d.y)));
         }
         reinterpret_cast<uint4*>(out)[i] = o.u;
     }
@@ -216,6 +216,67 @@ k_lrelu_bwd(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restric
     }
 }
 
+// ---- PixelNorm + LeakyReLU backward (generator half-block, layers.py:11-17 + generator.py:23,38) -----------------
+// o = t / n with t = lrelu(z), n = sqrt(mean_c t^2 + eps), inv = 1/n saved by the forward kernel.
+//   g_t = (g_o - o * mean_c(g_o * o)) * inv ;  g_z = g_t * (o > 0 ? 1 : 0.2) ;  gb[c] += sum_pixels g_z
+// one thread per pixel (channels contiguous in NHWC), two passes over its C channels
+__global__ void __launch_bounds__(256)
+k_pixelnorm_lrelu_bwd(const __nv_bfloat16* __restrict__ go, const __nv_bfloat16* __restrict__ o, const float* __restrict__ inv,
+                      __nv_bfloat16* __restrict__ gz, float* __restrict__ gb, int C, int64_t n_pixels) {
+    const int C8 = C >> 3;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pixels; p += (int64_t)gridDim.x * blockDim.x) {
+        const uint4* g4 = reinterpret_cast<const uint4*>(go + p * C);
+        const uint4* o4 = reinterpret_cast<const uint4*>(o + p * C);
+        float dot = 0.0f;
+        for (int c = 0; c < C8; ++c) {
+            Pack8 a, b; a.u = __ldg(g4 + c); b.u = __ldg(o4 + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 x = __bfloat1622float2(a.h[j]), y = __bfloat1622float2(b.h[j]);
+                dot = fmaf(x.x, y.x, dot); dot = fmaf(x.y, y.y, dot);
+            }
+        }
+        dot /= (float)C;
+        const float s = inv[p];
+        uint4* z4 = reinterpret_cast<uint4*>(gz + p * C);
+        for (int c = 0; c < C8; ++c) {
+            Pack8 a, b, r; a.u = __ldg(g4 + c); b.u = __ldg(o4 + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 x = __bfloat1622float2(a.h[j]), y = __bfloat1622float2(b.h[j]);
+                float t0 = (x.x - y.x * dot) * s, t1 = (x.y - y.y * dot) * s;
+                t0 *= y.x > 0.0f ? 1.0f : 0.2f; t1 *= y.y > 0.0f ? 1.0f : 0.2f;
+                r.h[j] = __floats2bfloat162_rn(t0, t1);
+            }
+            z4[c] = r.u;
+        }
+    }
+}
+
+// gb[c] += sum over pixels of g[.,c]  (bf16 NHWC); same thread <-> channel-chunk ownership as k_lrelu_bwd
+__global__ void __launch_bounds__(256)
+k_colsum(const __nv_bfloat16* __restrict__ g, float* __restrict__ gb, int C8, int64_t total, int64_t stride) {
+    extern __shared__ float s_gb[];
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = first; i < total; i += stride) {
+        Pack8 v; v.u = __ldg(reinterpret_cast<const uint4*>(g) + i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(v.h[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+    }
+    for (int i = threadIdx.x; i < C8 * 8; i += blockDim.x) s_gb[i] = 0.0f;
+    __syncthreads();
+    if (first < total) {
+        const int c0 = (int)(first % C8) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&s_gb[c0 + j], acc[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C8 * 8; i += blockDim.x) atomicAdd(&gb[i], s_gb[i]);
+}
+
 static unsigned grid_for(int64_t items, int per_block = 256, int cap = 148 * 16) {
     int64_t g = (items + per_block - 1) / per_block;
     return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
@@ -273,12 +334,30 @@ int mg_lrelu_bwd_bf16(const void* gy, const void* y, void* gz, float* gb, int64_
     return check_launch("k_lrelu_bwd");
 }
 
+int mg_pixelnorm_lrelu_bwd_bf16(const void* go, const void* o, const float* inv_norm, void* gz, float* gb,
+                                int64_t n_pixels, int C, mgStream stream) {
+    if (!go || !o || !inv_norm || !gz || n_pixels <= 0 || C < 8 || (C & 7) || C > 1024) return MG_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope ps("k_pixelnorm_lrelu_bwd", st);
+    k_pixelnorm_lrelu_bwd<<<grid_for(n_pixels, 256, 148 * 8), 256, 0, st>>>(
+        (const __nv_bfloat16*)go, (const __nv_bfloat16*)o, inv_norm, (__nv_bfloat16*)gz, gb, C, n_pixels);
+    if (gb) {
+        const int C8 = C / 8;
+        const int64_t total = n_pixels * C8;
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        while ((blocks * 256) % C8) ++blocks;
+        k_colsum<<<(unsigned)blocks, 256, (size_t)C * sizeof(float), st>>>((const __nv_bfloat16*)gz, gb, C8, total, blocks * 256);
+    }
+    return check_launch("k_pixelnorm_lrelu_bwd");
+}
+
 int mg_pool2_bf16(const void* in, void* out, int B, int Ho, int Wo, int C, int adjoint, mgStream stream) {
     if (!in || !out || B <= 0 || Ho <= 0 || Wo <= 0 || C < 8 || (C & 7)) return MG_ERR_BAD_ARG;
     const int64_t total = (int64_t)B * Ho * Wo * (C / 8);
     cudaStream_t st = (cudaStream_t)stream;
-    ProfScope ps(adjoint ? "k_unpool2" : "k_pool2", st);
-    if (!adjoint) k_pool2<<<grid_for(total), 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, Ho, Wo, C / 8, total);
+    ProfScope ps(adjoint == 1 ? "k_unpool2" : "k_pool2", st);
+    if (adjoint != 1) k_pool2<<<grid_for(total), 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, Ho, Wo, C / 8, total, adjoint == 2 ? 1.0f : 0.25f);
     else k_unpool2<<<grid_for(total), 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, Ho, Wo, C / 8, total);
     return check_launch("k_pool2");
 }

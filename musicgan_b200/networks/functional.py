@@ -113,13 +113,20 @@ class LReLUBwd(Function):
     @staticmethod
     def forward(ctx, gy, y):
         ctx.save_for_backward(y)
+        ctx.set_materialize_grads(False)       # an unused bias-gradient output arrives as None, not as zeros
         gz, gb = ops.lrelu_bwd(gy, y)
         return gz, gb
 
     @staticmethod
     def backward(ctx, ggz, ggb):
         (y,) = ctx.saved_tensors
-        g = ggz.float() + ggb.float()[None, :, None, None] if ggb is not None else ggz
+        if ggz is None and ggb is None:
+            return None, None
+        if ggb is None:                        # the usual double-backward case: the same masked multiply, same kernel
+            return LReLUBwd.apply(ggz, y)[0], None
+        g = ggb.float()[None, :, None, None].expand(y.shape)
+        if ggz is not None:
+            g = g + ggz.float()
         return (_act(g) * _lrelu_mask(y)), None
 
 
@@ -148,20 +155,17 @@ class GenConv(Function):
     @th.autograd.function.once_differentiable
     def backward(ctx, go):
         xa, w, o, inv = ctx.saved_tensors
-        of, gf = o.float(), go.float()
-        # PixelNorm backward: t = o * n ; g_t = (g_o - o * mean_c(g_o * o)) / n
-        gt = (gf - of * (gf * of).mean(dim=1, keepdim=True)) * inv[:, None]
-        gz = _act(gt * _lrelu_mask(of))
-        gx = gw = gb = None
+        # PixelNorm + LeakyReLU backward and the bias gradient in one kernel:
+        #   g_t = (g_o - o * mean_c(g_o * o)) / n ;  g_z = g_t * mask(o) ;  g_b = sum_pixels g_z
+        gz, gb = ops.pixelnorm_lrelu_bwd(go, o, inv, want_bias_grad=ctx.needs_input_grad[2])
+        gx = gw = None
         wf = w.float().contiguous()
         if ctx.needs_input_grad[0]:
             gx = ops.conv3x3(gz, wf, dgrad=True)
             if ctx.upsample_in:      # backward of the nearest upsampling folded into the read: sum of each 2x2 block
-                gx = _act(F.avg_pool2d(gx.float(), 2) * 4.0)
+                gx = ops.pool2(gx, sum_pool=True)
         if ctx.needs_input_grad[1]:
             gw = ops.conv3x3_wgrad(gz, xa, upsample_in=ctx.upsample_in)
-        if ctx.needs_input_grad[2]:
-            gb = gz.float().sum(dim=(0, 2, 3))
         return gx, gw, gb, None
 
 

@@ -36,6 +36,7 @@ def _l():
         l.mg_rgb_project_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]
         l.mg_rgb_wgrad_bf16.argtypes = [c_void_p] * 5 + [c_int, c_int64, c_int, c_void_p]
         l.mg_pool2_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
+        l.mg_pixelnorm_lrelu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]
         l.mg_lrelu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]
         l.mg_conv3x3_pack_weights.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]
         _declared = True
@@ -207,8 +208,9 @@ def rgb_wgrad(g: th.Tensor, mask_src, x: th.Tensor):
     return gw, gb
 
 
-def pool2(x: th.Tensor, adjoint: bool = False) -> th.Tensor:
-    """AvgPool2d(2,2) on bf16 channels_last, or its adjoint (0.25 * nearest x2 replication)."""
+def pool2(x: th.Tensor, adjoint: bool = False, sum_pool: bool = False) -> th.Tensor:
+    """AvgPool2d(2,2) on bf16 channels_last, its adjoint (0.25 * nearest x2 replication), or the 2x2 sum pooling
+    (backward of a nearest x2 upsampling)."""
     _check_act(x, "pool2 x")
     B, C, H, W = x.shape
     if adjoint:
@@ -219,8 +221,24 @@ def pool2(x: th.Tensor, adjoint: bool = False) -> th.Tensor:
         ho, wo = H // 2, W // 2
         out = th.empty((B, C, ho, wo), dtype=th.bfloat16, device=x.device, memory_format=th.channels_last)
     with th.cuda.device(x.device):
-        _lib.check(_l().mg_pool2_bf16(x.data_ptr(), out.data_ptr(), B, ho, wo, C, 1 if adjoint else 0, _stream()), "mg_pool2_bf16")
+        _lib.check(_l().mg_pool2_bf16(x.data_ptr(), out.data_ptr(), B, ho, wo, C, 1 if adjoint else (2 if sum_pool else 0), _stream()),
+                   "mg_pool2_bf16")
     return out
+
+
+def pixelnorm_lrelu_bwd(go: th.Tensor, o: th.Tensor, inv: th.Tensor, want_bias_grad: bool = True):
+    """Backward of LeakyReLU -> PixelNorm (saved normalised output `o`, saved 1/norm `inv`): (gz bf16, gb fp32)."""
+    go = as_act(go)
+    _check_act(o, "pixelnorm_lrelu_bwd o")
+    B, C, H, W = o.shape
+    inv = inv.float().contiguous()
+    gz = th.empty_like(o)
+    gb = th.zeros((C,), dtype=th.float32, device=o.device) if want_bias_grad else None
+    with th.cuda.device(o.device):
+        _lib.check(_l().mg_pixelnorm_lrelu_bwd_bf16(go.data_ptr(), o.data_ptr(), inv.data_ptr(), gz.data_ptr(),
+                                                    gb.data_ptr() if gb is not None else None, B * H * W, C, _stream()),
+                   "mg_pixelnorm_lrelu_bwd_bf16")
+    return gz, gb
 
 
 def lrelu_bwd(gy: th.Tensor, y: th.Tensor, want_bias_grad: bool = True):

@@ -134,3 +134,27 @@ def test_rgb_layers_and_pooling():
     assert rel_l2(p, F.avg_pool2d(a.float(), 2, 2)) <= 4e-3
     u = ops.pool2(p, adjoint=True)
     assert rel_l2(u, F.interpolate(p.float(), scale_factor=2.0, mode="nearest") * 0.25) <= 4e-3
+
+
+def test_pixelnorm_lrelu_backward_kernel():
+    """Fused backward of LeakyReLU -> PixelNorm against torch autograd (fp32) on the same bf16 inputs."""
+    from musicgan_b200.networks import ops
+    B, C, H, W = 2, 48, 12, 20
+    g = torch.Generator().manual_seed(21)
+    z = torch.randn(B, C, H, W, generator=g).cuda().requires_grad_(True)
+    t = F.leaky_relu(z, 0.2)
+    n = torch.sqrt(t.pow(2.0).mean(dim=1, keepdim=True) + 1e-8)
+    o = t / n
+    go = torch.randn(B, C, H, W, generator=g).cuda().bfloat16().contiguous(memory_format=torch.channels_last)
+    ob = o.detach().bfloat16().contiguous(memory_format=torch.channels_last)
+    inv = (1.0 / n.detach())[:, 0].contiguous()
+    gz, gb = ops.pixelnorm_lrelu_bwd(go, ob, inv)
+    # reference: differentiate with o, n replaced by their bf16 / fp32 saved values (the kernel's inputs)
+    of, gf = ob.float(), go.float()
+    ref = (gf - of * (gf * of).mean(dim=1, keepdim=True)) * inv[:, None] * torch.where(of > 0, 1.0, 0.2)
+    assert rel_l2(gz, ref) <= 4e-3
+    assert rel_l2(gb, ref.sum((0, 2, 3))) <= 4e-3
+    (auto,) = torch.autograd.grad(o, z, go.float())
+    assert rel_l2(gz, auto) <= 2e-2          # vs exact autograd: only the bf16 rounding of the saved output differs
+    s = ops.pool2(go, sum_pool=True)
+    assert rel_l2(s, F.avg_pool2d(go.float(), 2) * 4) <= 4e-3
