@@ -188,7 +188,29 @@ k_lrelu_bwd(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restric
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
     const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (int64_t i = first; i < total; i += stride) {
+    // 4 independent 16-byte loads per operand in flight per thread (memory-level parallelism)
+    int64_t i = first;
+    for (; i + 3 * stride < total; i += 4 * stride) {
+        Pack8 g[4], m[4], o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            g[u].u = __ldcs(reinterpret_cast<const uint4*>(gy) + i + u * stride);
+            m[u].u = __ldcs(reinterpret_cast<const uint4*>(y) + i + u * stride);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = __bfloat1622float2(g[u].h[j]);
+                const float2 mm = __bfloat1622float2(m[u].h[j]);
+                f.x *= mm.x > 0.0f ? 1.0f : 0.2f; f.y *= mm.y > 0.0f ? 1.0f : 0.2f;
+                o[u].h[j] = __floats2bfloat162_rn(f.x, f.y);
+                acc[2 * j] += f.x; acc[2 * j + 1] += f.y;
+            }
+            reinterpret_cast<uint4*>(gz)[i + u * stride] = o[u].u;
+        }
+    }
+    for (; i < total; i += stride) {
         Pack8 g, m, o;
         g.u = __ldg(reinterpret_cast<const uint4*>(gy) + i);
         m.u = __ldg(reinterpret_cast<const uint4*>(y) + i);
@@ -327,7 +349,8 @@ int mg_lrelu_bwd_bf16(const void* gy, const void* y, void* gz, float* gb, int64_
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope ps("k_lrelu_bwd", st);
     // stride = blocks * 256 must be a multiple of C8 so that a thread always meets the same channel chunk
-    int64_t blocks = (total + 255) / 256;
+    int64_t blocks = (total + 1023) / 1024;
+    if (blocks < 1) blocks = 1;
     if (blocks > 148 * 8) blocks = 148 * 8;
     while ((blocks * 256) % C8) ++blocks;
     k_lrelu_bwd<<<(unsigned)blocks, 256, (size_t)C * sizeof(float), st>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y, (__nv_bfloat16*)gz, gb, C8, total, blocks * 256);
