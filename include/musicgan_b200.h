@@ -131,11 +131,12 @@ int mg_conv3x3_pack_weights(const float* w_f32, int Cin, int Cout, int dgrad, vo
 int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* y, float* inv_norm,
                     int B, int H, int W, int Cin, int Cout, int flags, void* ws, size_t ws_bytes, mgStream stream);
 
-/* Weight gradient of the same convolution: dw[co][ci][ky][kx] += sum_{b,y,x} dy[b][y][x][co] *
+/* Weight gradient of the same convolution: dw[co][ci][ky][kx] = sum_{b,y,x} dy[b][y][x][co] *
  * xin[b][y+ky-1][x+kx-1][ci]   (xin = x, or x read through a nearest x2 upsampling when upsample_in != 0).
- * dy [B][H][W][Cout] bf16, x [B][H(/2)][W(/2)][Cin] bf16, dw fp32 [Cout][Cin][3][3] ACCUMULATED (caller zeroes).
- * `dbias` is reserved (pass NULL). */
-int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, float* dbias,
+ * dy [B][H][W][Cout] bf16, x [B][H(/2)][W(/2)][Cin] bf16, dw fp32 [Cout][Cin][3][3] OVERWRITTEN (deterministic
+ * two-stage reduction through `ws`, >= mg_conv3x3_wgrad_workspace_bytes). */
+size_t mg_conv3x3_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout);
+int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, void* ws, size_t ws_bytes,
                           int B, int H, int W, int Cin, int Cout, int upsample_in, mgStream stream);
 
 /* ------------------------------------------------------------------------------------------

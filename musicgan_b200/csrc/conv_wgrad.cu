@@ -3,14 +3,20 @@
 //   dw[co][ci][ky][kx] = sum_{b,y,x} dy[b][y][x][co] * xin[b][y+ky-1][x+kx-1][ci]
 //
 // (autograd's convolution_backward weight term for the nn.Conv2d of reference networks/generator.py:16-37 and
-// networks/discriminator.py:15-32).  Per 16 x 8 pixel tile both operands are staged once in the canonical
-// no-swizzle layout [channel chunk][pixel][8 ch] and read as MN-major UMMA operands (umma.cuh):
-//   A = dy tile   : M = co (8-channel chunks, SBO = chunk pitch), K = 128 tile pixels (dense, LBO = 128 B)
-//   B = xin halo  : N = ci,                                       K = the same pixels shifted by the tap:
-//                   16 pixels of one MMA = two tile rows -> start (2j+ky)*10+kx, LBO = one halo row (160 B)
-// so per tile 8 MMAs (M128 x N=Cin x K16) per tap accumulate D_tap[co][ci] in TMEM; the accumulators of all
-// tiles of the CTA stay in TMEM (9 taps x Cin columns, split in tap groups when that exceeds 512 columns) and
-// are flushed ONCE at the end with red.global.add.f32.
+// networks/discriminator.py:15-32).  GEMM view per 16 x 8 pixel tile (K = its 128 pixels):
+//
+//   D[(tap, ci)][co]  +=  A[(tap, ci)][k] * B[k][co]        A[(tap,ci)][k] = xin[pixel k shifted by tap][ci]
+//                                                           B[k][co]       = dy[pixel k][co]
+//
+// * the nine taps are STACKED IN M: rows r = tap * Cin + ci, cut in blocks of 128 rows, so the 128 rows of an MMA are
+//   full even when the channel counts are 16..48 (with M = output channels, as first written, 1/8..3/8 of the rows were
+//   used and 72 tiny MMAs per tile were issue bound);
+// * A lives in TMEM: transposer warps read the staged x halo ([channel chunk][halo position][8 ch], the same staging as
+//   the forward kernel) and write, per block, lane = row, column = pixel pair with tcgen05.st; the MMA takes A from
+//   TMEM (TS mode) and B = the dy tile MN-major from shared memory (no-swizzle canonical layout, umma.cuh);
+// * per tile and block 8 MMAs (M128 x N=Cout x K16); the accumulators of ALL tiles of a CTA stay in TMEM and are flushed
+//   once at the end into a per-CTA slice of the workspace; k_wgrad_reduce sums the slices into dw (deterministic, no
+//   atomics: 148 CTAs adding 9*Cin*Cout values each onto the same addresses cost 20-30 us per launch).
 #include "common.cuh"
 #include "umma.cuh"
 #include "conv_common.cuh"
@@ -19,42 +25,36 @@
 namespace mg {
 using namespace umma;
 
-constexpr int kDyPitch = 129;          // pixels per channel chunk of the staged dy tile (odd: spreads the transposer's banks)
-constexpr int kWgradMmaWarps = 3;      // taps are dealt round-robin to three MMA-issuing warps (72 MMAs per tile)
-constexpr int kXposeWarps = 8;         // dy tile: smem -> registers -> TMEM (A operand), two warps per TMEM lane quarter
+constexpr int kDyPitch = 129;          // pixels per channel chunk of the staged dy tile (B operand)
+constexpr int kWgradMmaWarps = 3;      // row blocks are dealt round-robin to three MMA-issuing warps
+constexpr int kXposeWarps = 8;         // x halo: smem -> registers -> TMEM (A operand), two warps per TMEM lane quarter
 constexpr int kWgradThreads = (kXposeWarps + 4 + kWgradMmaWarps) * 32;     // 480
+constexpr int kMaxBlocks = 4;          // row blocks per CTA (TMEM: nb * (Cout + 2 * 64) columns)
 
 struct WgradParams {
     const __nv_bfloat16* dy;    // [B][H][W][Cout]
     const __nv_bfloat16* x;     // [B][Hin][Win][Cin]
-    float* dw;                  // [Cout][Cin][3][3], accumulated atomically
+    float* part;                // per-CTA partial sums [gridDim.x][groups][nb][128 rows][Cout] (workspace)
     int B, H, W, Hin, Win, Cin, Cout, upsample;
     int tiles_x, tiles_y, n_tiles;
-    int taps_per_group, tmem_cols, stages, dy_chunks;
-    ItemDiv idiv_x;
+    int blocks_per_cta, n_blocks, tmem_cols, stages;
+    ItemDiv idiv_x, idiv_dy;
+    FastDiv div_cin;
     unsigned bar_offset;
     int tiles_per_img;
     FastDiv div_img, div_tx;
 };
 
-// Why the A operand lives in TMEM: with both operands in shared memory every one of the 72 MMAs of a tile re-reads the
-// 128-row (mostly padding) dy operand, 4 KB each -> ~290 KB of shared-memory reads per tile, which bounds the kernel
-// at ~2500 cycles/tile.  Here the dy tile is transposed ONCE per tile into TMEM (lane = output channel, column = pixel
-// pair) and all nine taps read it from there; shared memory only serves the small shifted x windows.
-// Output channel co sits on TMEM lane (co & 3) * 32 + (co >> 2) so that the four lane quarters (and therefore the
-// transposer warps) share the work evenly even when Cout is small.
 __global__ void __launch_bounds__(kWgradThreads, 1)
 k_conv3x3_wgrad(const WgradParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nch_x = p.Cin >> 3;
-    const int tap0 = blockIdx.y * p.taps_per_group;
-    const int ntaps = min(p.taps_per_group, 9 - tap0);
-    const int co0 = blockIdx.z * 128;
-    const int co_n = min(128, p.Cout - co0);
-    const int nch_dy = co_n >> 3;
+    const int nch_x = p.Cin >> 3, nch_dy = p.Cout >> 3;
+    const int blk0 = blockIdx.y * p.blocks_per_cta;
+    const int nb = min(p.blocks_per_cta, p.n_blocks - blk0);
+    const int rows_total = 9 * p.Cin;
 
-    const size_t dy_bytes = (size_t)p.dy_chunks * kDyPitch * 16;
+    const size_t dy_bytes = (size_t)nch_dy * kDyPitch * 16;
     const size_t x_bytes = (size_t)nch_x * kHaloPitch * 16;
     const size_t stage_bytes = dy_bytes + x_bytes;
     unsigned char* stage0 = smem;
@@ -68,7 +68,7 @@ k_conv3x3_wgrad(const WgradParams p) {
 
     constexpr int kProd0 = kXposeWarps, kMma0 = kXposeWarps + 4;
     if (tid == 0) {
-        for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], kWgradMmaWarps); }
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], kWgradMmaWarps + kXposeWarps * 32); }
         for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], kXposeWarps * 32); mbar_init(&a_empty[i], kWgradMmaWarps); }
         mbar_init(done, kWgradMmaWarps);
         mbar_fence_init();
@@ -78,12 +78,12 @@ k_conv3x3_wgrad(const WgradParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_a = tmem_base + (uint32_t)(p.tmem_cols - 128);      // two A buffers of 64 columns
+    const int a_cols = p.blocks_per_cta * 64;                                  // columns of one A buffer
+    const uint32_t tmem_a = tmem_base + (uint32_t)(p.tmem_cols - 2 * a_cols);  // two A buffers at the top
 
     if (warp >= kProd0 && warp < kMma0) {
-        // ================= producers =================
+        // ================= producers: dy tile + x halo of the tile, 16-byte cp.async =================
         const int pt = tid - kProd0 * 32;
-        const unsigned dy_magic = ((1u << 20) + nch_dy - 1) / nch_dy;
         int slot = 0; uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             mbar_wait(&empty[slot], ph ^ 1u);
@@ -94,10 +94,10 @@ k_conv3x3_wgrad(const WgradParams p) {
             const uint32_t s_dy = smem_u32(stage0 + slot * stage_bytes);
             const uint32_t s_x = s_dy + (uint32_t)dy_bytes;
             // dy tile: 128 pixels x nch_dy chunks (zero outside the image: those pixels must not contribute)
-            const __nv_bfloat16* dyb = p.dy + (size_t)b * p.H * p.W * p.Cout + co0;
+            const __nv_bfloat16* dyb = p.dy + (size_t)b * p.H * p.W * p.Cout;
             const int items_dy = 128 * nch_dy;
             for (int i = pt; i < items_dy; i += 128) {
-                const int pix = (int)(((unsigned)i * dy_magic) >> 20), c = i - pix * nch_dy;
+                const int pix = (int)(((unsigned)i * p.idiv_dy.magic) >> 20), c = i - pix * nch_dy;
                 const int oy = oy0 + (pix >> 3), ox = ox0 + (pix & 7);
                 const bool ok = oy < p.H && ox < p.W;
                 const void* src = ok ? (const void*)(reinterpret_cast<const uint4*>(dyb + ((size_t)oy * p.W + ox) * p.Cout) + c) : (const void*)p.dy;
@@ -119,10 +119,10 @@ k_conv3x3_wgrad(const WgradParams p) {
             if (++slot == p.stages) { slot = 0; ph ^= 1u; }
         }
     } else if (warp >= kMma0) {
-        // ================= MMA issue: warp kMma0 + w issues taps w, w + 3, w + 6 (A from TMEM, B from smem) =================
+        // ================= MMA issue: warp kMma0 + w issues row blocks w, w + 3 (A from TMEM, B = dy from smem) =================
         const int mw = warp - kMma0;
-        const uint32_t idesc = instr_desc_bf16(p.Cin, false, true);
-        const uint64_t b_desc0 = smem_desc(smem_u32(stage0) + (uint32_t)dy_bytes, kHaloW * 16u, kHaloPitch * 16u);
+        const uint32_t idesc = instr_desc_bf16(p.Cout, false, true);
+        const uint64_t b_desc0 = smem_desc(smem_u32(stage0), 128u, kDyPitch * 16u);    // MN-major: 8-pixel groups 128 B apart
         const uint32_t stage_units = (uint32_t)(stage_bytes >> 4);
         int slot = 0, buf = 0; uint32_t ph = 0, aph = 0, accum = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -131,17 +131,15 @@ k_conv3x3_wgrad(const WgradParams p) {
             tc_fence_after();
             if (lane == 0) {
                 const uint64_t db0 = b_desc0 + (uint64_t)(slot * stage_units);
-                const uint32_t a0 = tmem_a + buf * 64;
-                for (int tl = mw; tl < ntaps; tl += kWgradMmaWarps) {
-                    const int tap = tap0 + tl;
-                    const int ky = tap / 3, kx = tap - ky * 3;
-                    const uint32_t d = tmem_base + tl * p.Cin;
-                    uint64_t db = db0 + (uint64_t)(ky * kHaloW + kx);
+                for (int j = mw; j < nb; j += kWgradMmaWarps) {
+                    const uint32_t d = tmem_base + j * p.Cout;
+                    const uint32_t a0 = tmem_a + buf * a_cols + j * 64;
+                    uint64_t db = db0;
                     mma_bf16_ts(d, a0, db, idesc, accum);
 #pragma unroll
-                    for (int j = 1; j < 8; ++j) {
-                        db += 2 * kHaloW;
-                        mma_bf16_ts(d, a0 + j * 8, db, idesc, 1u);
+                    for (int s = 1; s < 8; ++s) {
+                        db += 16;                              // next 16 pixels of the dy tile
+                        mma_bf16_ts(d, a0 + s * 8, db, idesc, 1u);
                     }
                 }
                 mma_commit(&empty[slot]);
@@ -155,60 +153,72 @@ k_conv3x3_wgrad(const WgradParams p) {
         if (lane == 0) mma_commit(done);
         __syncwarp();
     } else {
-        // ================= transposers: dy tile smem -> TMEM A operand; then (warps 0-3) the final flush =================
+        // ================= transposers: shifted x windows, smem -> TMEM A operand; then the final flush =================
         const int quarter = warp & 3, khalf = warp >> 2;
-        const int co = 4 * lane + quarter;                  // local output channel owned by this TMEM lane
-        const bool row_ok = co < co_n;
+        const int L = quarter * 32 + lane;                   // TMEM lane == row within a block
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        // per block: where this lane's row (tap, ci) starts inside a staged x halo (bytes), or -1 if the row is padding
+        int row_off[kMaxBlocks];
+#pragma unroll
+        for (int j = 0; j < kMaxBlocks; ++j) {
+            const int r = (blk0 + j) * 128 + L;
+            row_off[j] = -1;
+            if (j < nb && r < rows_total) {
+                const int tap = fast_div(r, p.div_cin), ci = r - tap * p.Cin;
+                const int ky = tap / 3, kx = tap - ky * 3;
+                row_off[j] = ((ci >> 3) * kHaloPitch + ky * kHaloW + kx) * 16 + (ci & 7) * 2;
+            }
+        }
         int slot = 0, buf = 0; uint32_t ph = 0, aph = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             mbar_wait(&a_empty[buf], aph ^ 1u);
             mbar_wait(&full[slot], ph);
             tc_fence_after();
-            const unsigned char* s_dy = stage0 + slot * stage_bytes;
-            const unsigned char* row = s_dy + ((size_t)(co >> 3) * kDyPitch) * 16 + (co & 7) * 2;
-            const uint32_t ta = tmem_a + buf * 64 + khalf * 32 + lane_addr;
+            const unsigned char* s_x = stage0 + slot * stage_bytes + dy_bytes;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {                    // 4 groups of 8 columns = 16 pixels each
-                uint32_t r[8];
+            for (int j = 0; j < kMaxBlocks; ++j) {
+                if (j < nb) {
+                    const uint32_t ta = tmem_a + buf * a_cols + j * 64 + khalf * 32 + lane_addr;
+                    const bool ok = row_off[j] >= 0;
+                    const unsigned char* row = s_x + (ok ? row_off[j] : 0);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int pix = khalf * 64 + g * 16 + 2 * j;
-                    uint32_t lo = 0, hi = 0;
-                    if (row_ok) {
-                        lo = *reinterpret_cast<const uint16_t*>(row + (size_t)pix * 16);
-                        hi = *reinterpret_cast<const uint16_t*>(row + (size_t)(pix + 1) * 16);
+                    for (int g = 0; g < 4; ++g) {            // 8 columns = 16 pixels = tile rows 8*khalf + 2g, +1
+                        uint32_t r[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const int ry = khalf * 8 + g * 2 + (c >> 2), rx = (c & 3) * 2;
+                            const unsigned char* e = row + (ry * kHaloW + rx) * 16;
+                            uint32_t lo = 0, hi = 0;
+                            if (ok) { lo = *reinterpret_cast<const uint16_t*>(e); hi = *reinterpret_cast<const uint16_t*>(e + 16); }
+                            r[c] = lo | (hi << 16);
+                        }
+                        tmem_st8(ta + g * 8, r);
                     }
-                    r[j] = lo | (hi << 16);
                 }
-                tmem_st8(ta + g * 8, r);
             }
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&a_full[buf]);
+            mbar_arrive(&empty[slot]);       // this thread no longer reads the smem slot (the MMA warps commit theirs)
             if (++slot == p.stages) { slot = 0; ph ^= 1u; }
             if (++buf == 2) { buf = 0; aph ^= 1u; }
         }
-        {   // final flush: the two warps of a lane quarter split the taps; plain stores when no other CTA contributes
+        {   // final flush: every CTA writes its accumulators ONCE, with plain 16-byte stores, to its own slice of the
+            // workspace (k_wgrad_reduce sums the slices: no atomics, deterministic order, no pre-zeroed output)
             mbar_wait(done, 0);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + lane_addr;
-            const bool exclusive = gridDim.x == 1;
-            for (int tl = khalf; tl < ntaps; tl += 2) {
-                const int tap = tap0 + tl;
-                for (int c0 = 0; c0 < p.Cin; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(taddr + tl * p.Cin + c0, v);
-                    tmem_wait_ld();
-                    if (row_ok) {
-                        float* dst = p.dw + ((size_t)(co0 + co) * p.Cin + c0) * 9 + tap;
-                        if (exclusive) {
+            float* mine = p.part + ((size_t)(blockIdx.x * gridDim.y + blockIdx.y) * p.blocks_per_cta) * 128 * p.Cout;
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) dst[j * 9] = v[j];
-                        } else {
+            for (int j = 0; j < kMaxBlocks; ++j) {
+                if (j < nb && (j & 1) == khalf) {
+                    const uint32_t taddr = tmem_base + lane_addr + j * p.Cout;
+                    float4* dst = reinterpret_cast<float4*>(mine + ((size_t)j * 128 + L) * p.Cout);
+                    for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+                        float v[16];
+                        tmem_ld16(taddr + c0, v);
+                        tmem_wait_ld();
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) atomicAdd(dst + j * 9, v[j]);
-                        }
+                        for (int q = 0; q < 4; ++q) dst[(c0 >> 2) + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                     }
                 }
             }
@@ -219,40 +229,89 @@ k_conv3x3_wgrad(const WgradParams p) {
     if (warp == kMma0) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// dw[co][ci][tap] = sum over the gx CTAs of a group of part[cta][group][j][L][co], rows r = tap*Cin + ci = (g*nb + j)*128 + L
+// block = 8 warps x 32 consecutive outputs (consecutive co -> 128-byte rows); warp w sums CTAs w, w+8, ...; smem combine
+__global__ void __launch_bounds__(256)
+k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dw, int Cin, int Cout, int gx, int groups, int nb, FastDiv div_cin) {
+    __shared__ float red[8][33];
+    const int total = 9 * Cin * Cout;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + lane;
+    float s0 = 0.f, s1 = 0.f;
+    int r = 0, co = 0;
+    if (t < total) {
+        r = t / Cout; co = t - r * Cout;
+        const int blk = r >> 7, L = r & 127;
+        const int g = blk / nb, j = blk - g * nb;
+        const float* src = part + (((size_t)g * nb + j) * 128 + L) * Cout + co;
+        const size_t cta_stride = (size_t)groups * nb * 128 * Cout;
+        int x = w;
+        for (; x + 8 < gx; x += 16) { s0 += src[(size_t)x * cta_stride]; s1 += src[(size_t)(x + 8) * cta_stride]; }
+        if (x < gx) s0 += src[(size_t)x * cta_stride];
+    }
+    red[w][lane] = s0 + s1;
+    __syncthreads();
+    if (w == 0 && t < total) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][lane];
+        const int tap = fast_div(r, div_cin), ci = r - tap * Cin;
+        dw[((size_t)co * Cin + ci) * 9 + tap] = s;
+    }
+}
+
 }  // namespace mg
 
 using namespace mg;
 
-extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, float* dbias_unused,
+static void wgrad_grid(int n_tiles, int Cin, int Cout, int* nb_out, int* groups_out, int* gx_out) {
+    static int sm_count = 0;
+    if (!sm_count) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+    if (sm_count <= 0) sm_count = 148;
+    const int n_blocks = (9 * Cin + 127) / 128;
+    int nb = 512 / (Cout + 128); nb = nb > kMaxBlocks ? kMaxBlocks : (nb < 1 ? 1 : nb);
+    nb = nb > n_blocks ? n_blocks : nb;
+    while (nb > 1 && n_tiles * ((n_blocks + nb - 1) / nb) < sm_count) --nb;
+    int groups = (n_blocks + nb - 1) / nb;
+    nb = (n_blocks + groups - 1) / groups;                 // balance
+    groups = (n_blocks + nb - 1) / nb;
+    int gx = sm_count / groups;
+    gx = gx < 1 ? 1 : gx;
+    gx = gx > n_tiles ? n_tiles : gx;
+    *nb_out = nb; *groups_out = groups; *gx_out = gx;
+}
+
+extern "C" size_t mg_conv3x3_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cin < 16 || Cout < 16) return 0;
+    const int n_tiles = B * ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
+    int nb, groups, gx;
+    wgrad_grid(n_tiles, Cin, Cout, &nb, &groups, &gx);
+    return align_up((size_t)gx * groups * nb * 128 * Cout * sizeof(float), 256);
+}
+
+extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, void* ws, size_t ws_bytes,
                                      int B, int H, int W, int Cin, int Cout, int upsample_in, mgStream stream) {
-    (void)dbias_unused;
-    if (!dy || !x || !dw) return MG_ERR_BAD_ARG;
+    if (!dy || !x || !dw || !ws) return MG_ERR_BAD_ARG;
+    if (ws_bytes < mg_conv3x3_wgrad_workspace_bytes(B, H, W, Cin, Cout)) return MG_ERR_WORKSPACE;
+    if (((uintptr_t)ws & 15) != 0) return MG_ERR_BAD_ARG;
     if (B <= 0 || H <= 0 || W <= 0 || Cin < 16 || Cout < 16 || (Cin & 15) || (Cout & 15) || Cin > 256 || Cout > 256) return MG_ERR_UNSUPPORTED;
     if (upsample_in && ((H | W) & 1)) return MG_ERR_BAD_ARG;
     WgradParams p{};
-    p.dy = (const __nv_bfloat16*)dy; p.x = (const __nv_bfloat16*)x; p.dw = dw;
+    p.dy = (const __nv_bfloat16*)dy; p.x = (const __nv_bfloat16*)x; p.part = (float*)ws;
     p.B = B; p.H = H; p.W = W; p.Hin = upsample_in ? H / 2 : H; p.Win = upsample_in ? W / 2 : W; p.Cin = Cin; p.Cout = Cout;
     p.upsample = upsample_in ? 1 : 0;
     p.tiles_x = (W + kTileW - 1) / kTileW; p.tiles_y = (H + kTileH - 1) / kTileH; p.n_tiles = B * p.tiles_x * p.tiles_y;
-    // Tap groups: a CTA keeps taps_per_group x Cin accumulator columns plus two 64-column A buffers in its 512 TMEM
-    // columns; more taps than fit are split over blockIdx.y (balanced, e.g. 9 -> 5 + 4), each group re-reading the tiles.
-    int tpp = (512 - 128) / Cin; tpp = tpp > 9 ? 9 : (tpp < 1 ? 1 : tpp);
-    int groups = (9 + tpp - 1) / tpp;
-    static int sm_count_ = 0;
-    if (!sm_count_) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev); }
-    {   // small-spatial layers: too few tiles to fill the GPU -> spread the taps over more CTAs instead (fewer columns to
-        // flush per CTA, and with one CTA per group no atomics at all)
-        const int mb = (Cout + 127) / 128;
-        while (groups < 9 && p.n_tiles * groups * mb < sm_count_) groups = groups < 3 ? 3 : 9;
-    }
-    p.taps_per_group = (9 + groups - 1) / groups;
-    groups = (9 + p.taps_per_group - 1) / p.taps_per_group;
-    int cols = 32; while (cols < p.taps_per_group * Cin + 128) cols <<= 1;
+    // Row blocks: rows r = tap * Cin + ci in blocks of 128.  A CTA keeps nb * Cout accumulator columns plus two A buffers
+    // of nb * 64 columns in its 512 TMEM columns; more blocks than fit are split over blockIdx.y (each group re-reads
+    // the tiles).  When there are few tiles the blocks are spread over more CTAs anyway (small-spatial layers).
+    p.n_blocks = (9 * Cin + 127) / 128;
+    int nb, groups, gx;
+    wgrad_grid(p.n_tiles, Cin, Cout, &nb, &groups, &gx);
+    p.blocks_per_cta = nb;
+    int cols = 32; while (cols < nb * (Cout + 128)) cols <<= 1;
     p.tmem_cols = cols;
     const int occ = 1;
-    const int mblocks = (Cout + 127) / 128;
-    p.dy_chunks = (mblocks > 1 ? 128 : Cout) / 8;           // chunks of the widest M block
-    const size_t stage_bytes = (size_t)p.dy_chunks * kDyPitch * 16 + (size_t)(Cin / 8) * kHaloPitch * 16;
+    const size_t stage_bytes = (size_t)(Cout / 8) * kDyPitch * 16 + (size_t)(Cin / 8) * kHaloPitch * 16;
     int stages = kMaxStages;
     size_t smem = 0;
     for (; stages >= 1; --stages) {
@@ -263,6 +322,8 @@ extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, f
     if (stages < 1) return MG_ERR_UNSUPPORTED;
     p.stages = stages;
     p.idiv_x = make_item_div(Cin / 8);
+    p.idiv_dy = make_item_div(Cout / 8);
+    p.div_cin = make_fast_div(Cin);
     p.tiles_per_img = p.tiles_x * p.tiles_y;
     p.div_img = make_fast_div(p.tiles_per_img);
     p.div_tx = make_fast_div(p.tiles_x);
@@ -270,13 +331,15 @@ extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, f
     static int sm_count = 0;
     if (!sm_count) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
     cudaFuncSetAttribute(k_conv3x3_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int gx = sm_count * occ / (groups * mblocks);
-    gx = gx < 1 ? 1 : gx;
-    gx = gx > p.n_tiles ? p.n_tiles : gx;
     cudaStream_t st = (cudaStream_t)stream;
     {
         ProfScope ps("k_conv3x3_wgrad", st);
-        k_conv3x3_wgrad<<<dim3(gx, groups, mblocks), kWgradThreads, smem, st>>>(p);
+        k_conv3x3_wgrad<<<dim3(gx, groups, 1), kWgradThreads, smem, st>>>(p);
+    }
+    {
+        ProfScope ps("k_wgrad_reduce", st);
+        const int total = 9 * Cin * Cout;
+        k_wgrad_reduce<<<(total + 31) / 32, 256, 0, st>>>((const float*)ws, dw, Cin, Cout, gx, groups, nb, p.div_cin);
     }
     return check_launch("k_conv3x3_wgrad");
 }

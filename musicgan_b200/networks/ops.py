@@ -29,7 +29,9 @@ def _l():
         l.mg_conv3x3_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]
         if hasattr(l, "mg_conv3x3_wgrad_bf16"):
-            l.mg_conv3x3_wgrad_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p,
+            l.mg_conv3x3_wgrad_workspace_bytes.restype = c_size_t
+            l.mg_conv3x3_wgrad_workspace_bytes.argtypes = [c_int] * 5
+            l.mg_conv3x3_wgrad_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                                 c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
         c_int64 = ctypes.c_int64
         l.mg_rgb_expand_bf16.argtypes = [c_void_p] * 5 + [c_int, c_int64, c_int, c_int, c_void_p]
@@ -43,8 +45,8 @@ def _l():
     return l
 
 
-def _workspace(dev, nbytes: int) -> th.Tensor:
-    key = (dev.index, th.cuda.current_stream(dev).cuda_stream)
+def _workspace(dev, nbytes: int, tag: str = "pack") -> th.Tensor:
+    key = (tag, dev.index, th.cuda.current_stream(dev).cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = th.empty(max(nbytes, 1 << 20), dtype=th.uint8, device=dev)
@@ -139,11 +141,12 @@ def conv3x3_wgrad(dy: th.Tensor, x: th.Tensor, *, upsample_in=False) -> th.Tenso
     B, cout, H, W = dy.shape
     cin = x.shape[1]
     assert x.shape[0] == B and (x.shape[2] * (2 if upsample_in else 1), x.shape[3] * (2 if upsample_in else 1)) == (H, W)
-    dw = th.zeros((cout, cin, 3, 3), dtype=th.float32, device=dy.device)
+    dw = th.empty((cout, cin, 3, 3), dtype=th.float32, device=dy.device)      # overwritten: no zero fill needed
     l = _l()
     FLOPS["count"] += 2.0 * B * H * W * 9 * cin * cout
+    ws = _workspace(dy.device, l.mg_conv3x3_wgrad_workspace_bytes(B, H, W, cin, cout), "wgrad")
     with th.cuda.device(dy.device):
-        _lib.check(l.mg_conv3x3_wgrad_bf16(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), None,
+        _lib.check(l.mg_conv3x3_wgrad_bf16(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(),
                                            B, H, W, cin, cout, 1 if upsample_in else 0,
                                            th.cuda.current_stream().cuda_stream), "mg_conv3x3_wgrad_bf16")
     return dw
