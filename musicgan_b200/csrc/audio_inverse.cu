@@ -4,9 +4,10 @@
 // Replaces reference music_gan/audio/functions.py:97-137 (magn_phase_to_wav without the file write).
 //
 //   k_inv_magn_minmax  (m+1)/2 / bark  -> per-clip min / max                      (:111-113)
-//   k_inv_phase_scan   phase affine map, STRICTLY SEQUENTIAL float32 running sum along time per bin
-//                      (:115-118; SURVEY B.3: a parallel or fp64 scan only reaches 44 dB on coherent
-//                      phase), % 2pi, magn * (cos, sin) -> X[t][f] frame major      (:120-123)
+//   k_inv_phase_accumulate  phase affine map + STRICTLY SEQUENTIAL float32 running sum along time, one thread per
+//                      (clip, bin) chain (:115-118; SURVEY B.3: a parallel or fp64 scan only reaches 44 dB on
+//                      coherent phase) -- only the dependent FADD chain is serial
+//   k_inv_polar        % 2pi, magn * (cos, sin), [f][t] -> X[t][f] frame major, fully parallel   (:120-123)
 //   k_istft            per frame: half-complex -> packed 512-pt spectrum, inverse FFT (fft512.cuh),
 //                      Hann, overlap-add of 4 frames in registers (ascending frame order), divide by the
 //                      window envelope, trim n_fft/2 at both ends                    (:125-137)
@@ -58,43 +59,77 @@ k_inv_magn_minmax(const float* __restrict__ mp, int imgs, int W, const float* __
     }
 }
 
-// grid (4, n_clips), block 128: one warp = 32 bins x the whole time axis of one clip
+// :115-118 -- the phase affine map and the STRICTLY SEQUENTIAL float32 running sum along time, one thread per
+// (clip, bin) chain.  Only the cheap dependent chain lives here (one FADD per step); everything per element (fmodf,
+// sincosf, magnitude) is done in parallel by k_inv_polar.  acc [n_clips][imgs][512][W] fp32 (same layout as the input).
+// grid (4, n_clips), block 128
 __global__ void __launch_bounds__(128)
-k_inv_phase_scan(const float* __restrict__ mp, int imgs, int W, const float* __restrict__ bark,
-                 const int* __restrict__ keys, float2* __restrict__ X) {
-    __shared__ float tp[4][32][33];
-    __shared__ float tm[4][32][33];
-    const int clip = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int f0 = (blockIdx.x * 4 + warp) * 32;
-    const int64_t Wt = (int64_t)imgs * W;
-    const float range = __fsub_rn(key_float(keys[clip * 4 + 1]), key_float(keys[clip * 4 + 0]));   // :113
-    const float gain = bark[f0 + lane];
+k_inv_phase_accumulate(const float* __restrict__ mp, int imgs, int W, float* __restrict__ acc_out) {
+    const int clip = blockIdx.y, f = blockIdx.x * 128 + threadIdx.x;
     float acc = 0.0f;
-    for (int64_t tt0 = 0; tt0 < Wt; tt0 += 32) {
-        const int64_t tt = tt0 + lane;
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-            float p = 0.0f, m = 0.0f;
-            if (tt < Wt) {
-                p = __ldcs(mp + img_index(clip, imgs, W, 1, f0 + r, tt));
-                m = __ldcs(mp + img_index(clip, imgs, W, 0, f0 + r, tt));
+    bool first = true;
+    const bool vec = (W & 3) == 0;
+    for (int i = 0; i < imgs; ++i) {
+        const float* src = mp + ((((int64_t)clip * imgs + i) * 2 + 1) * kIBins + f) * (int64_t)W;
+        float* dst = acc_out + (((int64_t)clip * imgs + i) * kIBins + f) * (int64_t)W;
+        int w = 0;
+        if (vec) {
+            for (; w + 8 <= W; w += 8) {
+                const float4 a = __ldcs(reinterpret_cast<const float4*>(src + w)), b = __ldcs(reinterpret_cast<const float4*>(src + w + 4));
+                float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float p = __fsub_rn(__fmul_rn(__fmul_rn(__fdiv_rn(__fadd_rn(v[j], 1.0f), 2.0f), 2.0f), kPiF), kPiF);
+                    acc = first ? p : __fadd_rn(acc, p);
+                    first = false;
+                    v[j] = acc;
+                }
+                *reinterpret_cast<float4*>(dst + w) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(dst + w + 4) = make_float4(v[4], v[5], v[6], v[7]);
             }
-            tp[warp][r][lane] = p; tm[warp][r][lane] = m;
         }
-        __syncwarp();
-        const int n = (int)min((int64_t)32, Wt - tt0);
-        for (int j = 0; j < n; ++j) {
-            // :115  (phase + 1.) / 2. * 2. * pi - pi, every op rounded to float32
-            float p = tp[warp][lane][j];
-            p = __fsub_rn(__fmul_rn(__fmul_rn(__fdiv_rn(__fadd_rn(p, 1.0f), 2.0f), 2.0f), kPiF), kPiF);
-            acc = (tt0 + j == 0) ? p : __fadd_rn(acc, p);                  // :117-118 sequential fp32 sum
-            const float ph = remainder_pos(acc, kTwoPiF);                   // :120
+        for (; w < W; ++w) {
+            const float p = __fsub_rn(__fmul_rn(__fmul_rn(__fdiv_rn(__fadd_rn(src[w], 1.0f), 2.0f), 2.0f), kPiF), kPiF);
+            acc = first ? p : __fadd_rn(acc, p);
+            first = false;
+            dst[w] = acc;
+        }
+    }
+}
+
+// :111-113,120-123 -- per element: magnitude de-normalisation, phase % 2pi, magn * (cos, sin); [f][t] tiles are transposed
+// through shared memory so that X[t][f] (frame major, what k_istft reads) is written in full lines.
+// grid (ceil(Wt / 32), 16, n_clips), block 256
+__global__ void __launch_bounds__(256)
+k_inv_polar(const float* __restrict__ mp, const float* __restrict__ acc_in, int imgs, int W, const float* __restrict__ bark,
+            const int* __restrict__ keys, float2* __restrict__ X) {
+    __shared__ float tp[32][33];
+    __shared__ float tm[32][33];
+    const int clip = blockIdx.z, f0 = blockIdx.y * 32;
+    const int64_t Wt = (int64_t)imgs * W, tt0 = (int64_t)blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float range = __fsub_rn(key_float(keys[clip * 4 + 1]), key_float(keys[clip * 4 + 0]));   // :113
+    for (int r = ty; r < 32; r += 8) {              // r = bin within the tile, tx = time within the tile
+        const int64_t tt = tt0 + tx;
+        float a = 0.0f, m = 0.0f;
+        if (tt < Wt) {
+            const int i = (int)(tt / W), w = (int)(tt % W);
+            a = __ldcs(acc_in + (((int64_t)clip * imgs + i) * kIBins + f0 + r) * (int64_t)W + w);
+            m = __ldcs(mp + img_index(clip, imgs, W, 0, f0 + r, tt));
+        }
+        tp[r][tx] = a; tm[r][tx] = m;
+    }
+    __syncthreads();
+    const float gain = bark[f0 + tx];
+    for (int c = ty; c < 32; c += 8) {              // c = time within the tile, tx = bin within the tile
+        const int64_t tt = tt0 + c;
+        if (tt < Wt) {
+            const float ph = remainder_pos(tp[tx][c], kTwoPiF);                   // :120
             float sn, cs;
             sincosf(ph, &sn, &cs);
-            const float m = __fdiv_rn(magn_unscaled(tm[warp][lane][j], gain), range);
-            X[((int64_t)clip * Wt + tt0 + j) * kIBins + f0 + lane] = make_float2(__fmul_rn(m, cs), __fmul_rn(m, sn));
+            const float m = __fdiv_rn(magn_unscaled(tm[tx][c], gain), range);
+            X[((int64_t)clip * Wt + tt) * kIBins + f0 + tx] = make_float2(__fmul_rn(m, cs), __fmul_rn(m, sn));
         }
-        __syncwarp();
     }
 }
 
@@ -211,14 +246,15 @@ k_istft(const float2* __restrict__ X, int64_t Wt, const float* __restrict__ wind
     }
 }
 
-struct InverseWs { float2* X; int* keys; size_t bytes; };
+struct InverseWs { float2* X; float* acc; int* keys; size_t bytes; };
 static InverseWs carve_inverse_ws(void* ws, int n_clips, int64_t Wt) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_x = take((size_t)n_clips * Wt * kIBins * sizeof(float2));
+    const size_t o_a = take((size_t)n_clips * Wt * kIBins * sizeof(float));
     const size_t o_k = take((size_t)n_clips * 4 * sizeof(int));
     InverseWs w; char* b = (char*)ws;
-    w.X = (float2*)(b + o_x); w.keys = (int*)(b + o_k); w.bytes = off;
+    w.X = (float2*)(b + o_x); w.acc = (float*)(b + o_a); w.keys = (int*)(b + o_k); w.bytes = off;
     return w;
 }
 
@@ -252,8 +288,10 @@ int mg_istft_from_magif_f32(const float* magn_phase, int n_clips, int imgs_per_c
     const unsigned gx = (unsigned)max((int64_t)1, min((int64_t)592, per_img / 1024));
     { ProfScope ps("k_inv_magn_minmax", st);
       k_inv_magn_minmax<<<dim3(gx, n_clips), 256, 0, st>>>(magn_phase, imgs_per_clip, width, bark_gain, w.keys); }
-    { ProfScope ps("k_inv_phase_scan", st);
-      k_inv_phase_scan<<<dim3(4, n_clips), 128, 0, st>>>(magn_phase, imgs_per_clip, width, bark_gain, w.keys, w.X); }
+    { ProfScope ps("k_inv_phase_accumulate", st);
+      k_inv_phase_accumulate<<<dim3(4, n_clips), 128, 0, st>>>(magn_phase, imgs_per_clip, width, w.acc); }
+    { ProfScope ps("k_inv_polar", st);
+      k_inv_polar<<<dim3((unsigned)((Wt + 31) / 32), 16, n_clips), 256, 0, st>>>(magn_phase, w.acc, imgs_per_clip, width, bark_gain, w.keys, w.X); }
     const int64_t n_hops = Wt - 1;
     const unsigned gh = (unsigned)((n_hops + kIstftWarps * kHopsPerWarp - 1) / (kIstftWarps * kHopsPerWarp));
     static bool attr_done = false;
