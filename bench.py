@@ -241,18 +241,68 @@ def run_transform_reference(args, rank):
     }
 
 
+# ------------------------------------------------------------------------------------------------
+# generate workload (BASELINE config 5): G inference on a wide latent + inverse transform, clips sharded over the ranks
+# ------------------------------------------------------------------------------------------------
+def run_generate(args, rank, world, local):
+    from musicgan_b200 import _lib, audio, networks
+    nb_vec, per_gpu, sub = 4, args.gen_clips, 16
+    torch.manual_seed(0)
+    gen = networks.Generator(32, end_layer=7).eval().cuda()
+    z_all = torch.randn(per_gpu, 32, 2, 2 * nb_vec, device="cuda")
+    host_out = torch.empty(sub, 256 * (512 * nb_vec - 1)).pin_memory()
+
+    def step(e2e=False):
+        with torch.no_grad():
+            for lo in range(0, per_gpu, sub):
+                img = gen(z_all[lo:lo + sub], 1.0)
+                wav = audio.magn_phase_to_wave_batch(img, 1)
+                if e2e:
+                    host_out[: wav.size(0)].copy_(wav, non_blocking=True)
+
+    _lib.profile_enable(True)
+    with ClockSampler(local) as cs:
+        ms = timed_region(step, args.steps, args.warmup, world)
+    prof = _lib.profile_collect()
+    _lib.profile_enable(False)
+    value = world * per_gpu * args.steps / (ms * 1e-3)
+    ms2 = timed_region(lambda: step(True), max(1, min(args.steps, 5)), 1, world)
+    e2e = world * per_gpu * max(1, min(args.steps, 5)) / (ms2 * 1e-3)
+    if rank != 0:
+        return None
+    pk = peaks()
+    frames = per_gpu * 512 * nb_vec * args.steps
+    inv_ms = sum(v[0] for k, v in prof.items() if k.startswith("k_inv") or k == "k_istft")
+    achieved = frames * BYTES_PER_FRAME / (inv_ms * 1e-3) / 1e9 if inv_ms > 0 else 0.0
+    return {
+        "metric": "generated clips/s (G inference + IF->phase->iSTFT)", "value": value, "unit": "clips/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16 (G) / f32 (inverse)", "data": "synthetic",
+        "config": {"workload": f"generate (BASELINE config 5): {per_gpu} clips/GPU/step of {512 * nb_vec} frames (11.9 s), sub-batches of {sub}",
+                   "parallelism": f"clips sharded over {world} GPU(s), no collective"},
+        "clocks": cs.summary(),
+        "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": per_gpu * 256 * (512 * nb_vec - 1) * 4},
+        "gpu_launches": int(sum(c for _, c in prof.values())),
+        "roofline": {"bound": "hbm", "kernel": "inverse transform kernels (k_inv_* + k_istft)", "achieved": achieved, "peak": pk["hbm"],
+                     "unit": "GB/s", "frac": achieved / pk["hbm"], "peak_source": pk["src"], "traffic": None,
+                     "kernel_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}},
+        "cpu_baseline": None,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("MG_BENCH_WORKLOAD", "both"), choices=["both", "transform", "train"],
+    ap.add_argument("--workload", default=os.environ.get("MG_BENCH_WORKLOAD", "both"), choices=["both", "transform", "train", "generate"],
                     help="both (default): the train workload (BASELINE config 2) is the headline line, the transform workload "
                          "(config 1) rides along under 'secondary'")
     ap.add_argument("--clips", type=int, default=64, help="clips per GPU per step (transform workload)")
     ap.add_argument("--batch", type=int, default=8, help="samples per GPU per step (train workload)")
     ap.add_argument("--e2e-clips", type=int, default=16)
+    ap.add_argument("--gen-clips", type=int, default=128, help="clips per GPU per step (generate workload)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -275,6 +325,8 @@ def main():
 
     rank, world, local = dist_setup(args.gpus)
     res = None
+    if args.workload == "generate":
+        res = run_generate(args, rank, world, local)
     if args.workload in ("both", "train"):
         from musicgan_b200 import bench_train
         res = bench_train.run(args, rank, world, local, timed_region, ClockSampler, peaks)
