@@ -160,14 +160,20 @@ int mg_rgb_project_bf16(const void* a, const float* w2, int row_stride, int col_
                         float* out, int B, int64_t HW, int C, int act, mgStream stream);
 int mg_rgb_wgrad_bf16(const void* g, const void* mask_src, const float* x, float* gw, float* gb, int B, int64_t HW, int C, mgStream stream);
 int mg_pool2_bf16(const void* in, void* out, int B, int Ho, int Wo, int C, int adjoint, mgStream stream);
-/* LeakyReLU(0.2) backward fused with the bias gradient: gz = gy * mask(y) (bf16 NHWC), gb[c] += sum over pixels of gz
- * (fp32, caller zeroes, may be NULL).  (backward of the Conv2d + LeakyReLU pairs, discriminator.py:15-22,26-33) */
+/* Scratch of the per-channel sums below: one row of C partial sums per thread block, summed by a second small kernel in
+ * a fixed order (deterministic, no atomics). */
+size_t mg_colsum_workspace_bytes(int C);
+/* LeakyReLU(0.2) backward fused with the bias gradient: gz = gy * mask(y) (bf16 NHWC), gb[c] = sum over pixels of gz
+ * (fp32, OVERWRITTEN, may be NULL; needs ws of mg_colsum_workspace_bytes(C)).
+ * (backward of the Conv2d + LeakyReLU pairs, discriminator.py:15-22,26-33) */
+int mg_lrelu_bwd_bf16(const void* gy, const void* y, void* gz, float* gb, void* ws, size_t ws_bytes,
+                      int64_t n_pixels, int C, mgStream stream);
 /* PixelNorm + LeakyReLU backward of a generator half-block (layers.py:11-17 after generator.py:23,38):
  * go, o [n_pixels][C] bf16 (o = the normalised forward output), inv_norm [n_pixels] fp32 (from mg_conv3x3_bf16 flag 2)
- * -> gz [n_pixels][C] bf16 = gradient w.r.t. the convolution output (+bias), gb[c] += sum over pixels (may be NULL). */
-int mg_pixelnorm_lrelu_bwd_bf16(const void* go, const void* o, const float* inv_norm, void* gz, float* gb,
+ * -> gz [n_pixels][C] bf16 = gradient w.r.t. the convolution output (+bias), gb[c] = sum over pixels (OVERWRITTEN, may be
+ * NULL; needs ws of mg_colsum_workspace_bytes(C)). */
+int mg_pixelnorm_lrelu_bwd_bf16(const void* go, const void* o, const float* inv_norm, void* gz, float* gb, void* ws, size_t ws_bytes,
                                 int64_t n_pixels, int C, mgStream stream);
-int mg_lrelu_bwd_bf16(const void* gy, const void* y, void* gz, float* gb, int64_t n_pixels, int C, mgStream stream);
 
 /* ------------------------------------------------------------------------------------------
  * Test-only probe of the tcgen05 / TMEM conventions the convolution kernels rely on (one tile).

@@ -112,7 +112,7 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
     step(); th.cuda.synchronize()
     it[0] = 0
     _lib.profile_enable(True)
-    ops.FLOPS["count"] = 0.0
+    ops.FLOPS.update(count=0.0, bytes=0.0, launches=[])
     for _ in range(prof_iters):
         step()
     th.cuda.synchronize()
@@ -122,6 +122,8 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
     scale = args.steps / prof_iters
     prof = {k: (v[0] * scale, int(round(v[1] * scale))) for k, v in prof.items()}
     conv_flops_timed = ops.FLOPS["count"] * scale
+    conv_bytes_timed = ops.FLOPS["bytes"] * scale
+    conv_launch_list, ops.FLOPS["launches"] = ops.FLOPS["launches"], None
     value = world * args.steps / (ms * 1e-3)
 
     # end to end: real batch from pinned host memory every step, loss read back
@@ -143,7 +145,16 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
     conv_names = ("k_conv3x3_fprop", "k_conv3x3_dgrad", "k_conv3x3_wgrad")
     conv_ms = sum(prof.get(n, (0.0, 0))[0] for n in conv_names)
     conv_launches = sum(prof.get(n, (0.0, 0))[1] for n in conv_names)
-    achieved = conv_flops_timed / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    conv_s = conv_ms * 1e-3
+    tf_achieved = conv_flops_timed / conv_s / 1e12 if conv_ms > 0 else 0.0
+    gb_achieved = conv_bytes_timed / conv_s / 1e9 if conv_ms > 0 else 0.0
+    # which roof binds: the stage-7 layers have 16..160 channels, so most launches sit left of the ridge point
+    # (2*9*Cin*Cout FLOP per 2*(Cin+Cout) bytes).  The per-launch bound is max(flops / TF, bytes / HBM); its sum over the
+    # launches of a step is the time a perfect kernel would need
+    t_tensor = conv_flops_timed / (pk["tf_sus"] * 1e12)
+    t_hbm = conv_bytes_timed / (pk["hbm"] * 1e9)
+    t_bound = sum(max(f / (pk["tf_sus"] * 1e12), b / (pk["hbm"] * 1e9)) for f, b in conv_launch_list) * scale
+    hbm_bound = t_hbm >= t_tensor
     step_tf = batch * FLOP_PER_ITER * args.steps / (ms * 1e-3) / 1e12
     cpu = cpu_baseline(batch)
     return {
@@ -158,8 +169,15 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
         "clocks": cs.summary(),
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(reals_host[0].numel() * 4), "d2h_bytes_per_step": 4},
         "gpu_launches": int(sum(c for _, c in prof.values())),
-        "roofline": {"bound": "tensor", "kernel": "k_conv3x3 (fprop+dgrad+wgrad, all layers)", "achieved": achieved, "peak": pk["tf_sus"],
-                     "unit": "TFLOP/s", "frac": achieved / pk["tf_sus"], "peak_source": pk["src"] + " (sustained bf16)", "traffic": None,
+        "roofline": {"bound": "hbm" if hbm_bound else "tensor", "kernel": "k_conv3x3 (fprop+dgrad+wgrad, all layers)",
+                     "achieved": gb_achieved if hbm_bound else tf_achieved, "peak": pk["hbm"] if hbm_bound else pk["tf_sus"],
+                     "unit": "GB/s" if hbm_bound else "TFLOP/s",
+                     "frac": (gb_achieved / pk["hbm"]) if hbm_bound else (tf_achieved / pk["tf_sus"]),
+                     "peak_source": pk["src"] + " (sustained)", "traffic": None,
+                     "tensor": {"achieved": tf_achieved, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": tf_achieved / pk["tf_sus"]},
+                     "hbm": {"achieved": gb_achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": gb_achieved / pk["hbm"],
+                             "bytes": "x read once + y written once per launch (wgrad: dy + x read), weights excluded"},
+                     "per_launch_bound_frac": t_bound / conv_s if conv_ms > 0 else 0.0,
                      "kernel_timing": "event pairs around every library kernel in an eager pass of the same 5-iteration schedule "
                                       "right after the timed region (graph replays cannot carry event pairs)" if use_graphs else "timed region",
                      "conv_ms_per_step": conv_ms / args.steps, "conv_launches_per_step": conv_launches / args.steps,

@@ -37,23 +37,35 @@ struct ConvParams {
     float* inv_norm;             // [B][H][W] 1/sqrt(mean_c(v^2)+eps) (pixelnorm, optional)
     int B, H, W, Hin, Win, Cin, Cout;
     int upsample, lrelu, pixelnorm;
+    float slope;                 // LeakyReLU as max(v, slope * v): 0.2, or 1.0 for the identity
     int tiles_x, tiles_y, n_tiles;
     int Nt, stages, tmem_cols, tiles_per_img;
+    int n_acc, acc_stride;       // accumulators in flight in TMEM (2..8) and their column pitch
+    int mb, blk_stride;          // M blocks (16 x 8 pixels each, stacked vertically) per pipeline step; TMEM columns per block
+    int halo_pos, halo_pitch;    // (16 mb + 2) * 10 halo positions per step; pitch of one 8-channel plane of a slot
     ItemDiv idiv;
     FastDiv div_img, div_tx;
     int consumer_fence;
+    int ablate;                  // debug (MG_CONV_ABLATE): 1 no halo copies, 2 no MMAs, 4 no epilogue work, 8 no global stores
     int epi_warps;               // 4 or 8 epilogue warps; producers are the next 4 warps, then the MMA warp
 };
 
 // warp roles: [0, E) epilogue (E = 4, or 8 = two per TMEM lane quarter with half the columns each), [E, E+4) producers,
 // warp E+4 MMA issue + TMEM alloc.  Block size (E + 5) * 32.
 constexpr int kConvThreads = 13 * 32;                // upper bound (E = 8)
+constexpr int kMaxAcc = 8;
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-__global__ void __launch_bounds__(kConvThreads, 2)
+// kPN: PixelNorm in the epilogue.  kBA: bias + LeakyReLU in the epilogue (fprop); false for dgrad, whose epilogue is a
+// plain fp32 -> bf16 store.  The bias is not added by the epilogue threads: it enters the accumulator through one extra
+// K = 16 MMA per tile whose A operand is a constant tile (columns 0 and 1 = 1.0) and whose B operand holds the bias
+// split in two bf16 terms (hi + lo: 16 mantissa bits) in K rows 0 and 1.
+// kOcc4: the 9-warp shape compiled for 4 CTAs per SM (56 registers per thread, a shorter chunk table in the producers).
+template <bool kPN, bool kBA, bool kOcc4>
+__global__ void __launch_bounds__(kOcc4 ? 288 : kConvThreads, kOcc4 ? 4 : 2)
 k_conv3x3(const ConvParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -63,22 +75,22 @@ k_conv3x3(const ConvParams p) {
     const int nt = min(p.Nt, p.Cout - n0);
     const int kEpiWarps = p.epi_warps, kProdWarp0 = kEpiWarps, kMmaWarp = kEpiWarps + 4;
 
-    uint4* sW = reinterpret_cast<uint4*>(smem);
-    uint4* sA0 = sW + 9 * nch * nt;
-    float* sBias = reinterpret_cast<float*>(sA0 + (size_t)p.stages * nch * kHaloPitch);      // 16-byte aligned
-    float* sPart = sBias + ((nt + 3) & ~3);                                                  // [2][128] PixelNorm partial sums
+    uint4* sW = reinterpret_cast<uint4*>(smem);                    // [9 taps][nch][nt] + bias pseudo-tap [2][nt]
+    uint4* sOnes = sW + (9 * nch + 2) * nt;                        // [2][128]: the constant A tile of the bias MMA
+    uint4* sA0 = sOnes + 256;
+    float* sPart = reinterpret_cast<float*>(sA0 + (size_t)p.stages * nch * p.halo_pitch);      // [2][128] PixelNorm partial sums
     uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + 256);
     uint64_t* full_a = bars;                       // [kMaxStages]
     uint64_t* empty_a = bars + kMaxStages;         // [kMaxStages]
-    uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]
-    uint64_t* tmem_empty = tmem_full + 2;          // [2]
-    uint64_t* w_full = tmem_full + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 5);
+    uint64_t* tmem_full = bars + 2 * kMaxStages;   // [kMaxAcc]
+    uint64_t* tmem_empty = tmem_full + kMaxAcc;    // [kMaxAcc]
+    uint64_t* w_full = tmem_full + 2 * kMaxAcc;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
     if (tid == 0) {
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full_a[i], 128); mbar_init(&empty_a[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps * 32); }
-        mbar_init(w_full, 128);
+        for (int i = 0; i < kMaxAcc; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
+        mbar_init(w_full, 256);           // per producer thread: its cp.async group + one plain (release) arrive
         mbar_fence_init();
     }
     if (warp == kMmaWarp) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -86,7 +98,7 @@ k_conv3x3(const ConvParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int acc_stride = p.tmem_cols >> 1;
+    const int acc_stride = p.acc_stride;
 
     if (warp >= kProdWarp0 && warp < kMmaWarp) {
         // ================= producers =================
@@ -98,28 +110,41 @@ k_conv3x3(const ConvParams p) {
             // load loop here used to dominate the run time of the small-spatial layers)
             const uint32_t sw_addr = smem_u32(sW);
             for (int i = pt; i < total; i += 128) cp_async16(sw_addr + (uint32_t)i * 16u, src + i, 16u);
-            for (int i = pt; i < nt; i += 128) sBias[i] = p.bias ? p.bias[n0 + i] : 0.0f;
+            if (kBA) {
+                uint4* sB = sW + 9 * nch * nt;
+                for (int i = pt; i < nt; i += 128) {
+                    const float bv = p.bias ? p.bias[n0 + i] : 0.0f;
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(bv), lo = __float2bfloat16_rn(bv - __bfloat162float(hi));
+                    sB[i] = make_uint4((uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16), 0u, 0u, 0u);
+                    sB[nt + i] = make_uint4(0u, 0u, 0u, 0u);
+                }
+                sOnes[pt] = make_uint4(0x3F803F80u, 0u, 0u, 0u);          // bf16 (1.0, 1.0) in K columns 0 and 1
+                sOnes[128 + pt] = make_uint4(0u, 0u, 0u, 0u);
+                fence_proxy_async();                                      // st.shared operands -> tensor core reads
+            }
             cp_async_arrive(w_full);
+            mbar_arrive(w_full);
         }
-        const int items = kHaloPos * nch;
+        const int items = p.halo_pos * nch;
         // Per-thread item table, built once: for each 16-byte chunk this thread copies per tile, where it comes from
         // relative to the tile origin (tile independent, because tiles start at even rows / columns), where it goes in
         // the halo slot, and its halo coordinates (for the image-border test).  Up to kItemRegs items live in registers;
         // wider layers (Cin > 64) take the generic path for the remaining items.
-        constexpr int kItemRegs = 12;
+        constexpr int kItemRegs = kOcc4 ? 6 : 12;
         int rel[kItemRegs];            // source offset in uint4 units from the tile origin
-        uint32_t dsto[kItemRegs];      // (hy << 24) | (hx << 16) | smem chunk index
-        const int sy_step = p.upsample ? kTileH / 2 : kTileH, sx_step = p.upsample ? kTileW / 2 : kTileW;
+        uint32_t meta[kItemRegs];      // (hy << 25) | (hx << 21) | byte offset in the halo slot
+        const int rows = kTileH * p.mb;
+        const int sy_step = p.upsample ? rows / 2 : rows, sx_step = p.upsample ? kTileW / 2 : kTileW;
 #pragma unroll
         for (int k = 0; k < kItemRegs; ++k) {
             const int i = pt + k * 128;
-            rel[k] = 0; dsto[k] = 0xFFFFFFFFu;
+            rel[k] = 0; meta[k] = 0xFFFFFFFFu;
             if (i < items) {
                 const int pos = (int)(((unsigned)i * p.idiv.magic) >> 20), c = i - pos * nch;
                 const int hy = (pos * 6554) >> 16, hx = pos - hy * kHaloW;
                 const int ry = p.upsample ? ((hy - 1) >> 1) : hy - 1, rx = p.upsample ? ((hx - 1) >> 1) : hx - 1;
                 rel[k] = (ry * p.Win + rx) * nch + c;
-                dsto[k] = ((uint32_t)hy << 24) | ((uint32_t)hx << 16) | (uint32_t)(c * kHaloPitch + pos);
+                meta[k] = ((uint32_t)hy << 25) | ((uint32_t)hx << 21) | ((uint32_t)(c * p.halo_pitch + pos) * 16u);
             }
         }
         int slot = 0; uint32_t ph = 0;
@@ -128,18 +153,27 @@ k_conv3x3(const ConvParams p) {
             const int b = fast_div(tile, p.div_img);
             const int tr = tile - b * p.tiles_per_img;
             const int tyi = fast_div(tr, p.div_tx), txi = tr - tyi * p.tiles_x;
-            const int ty0 = tyi * kTileH - 1, tx0 = txi * kTileW - 1;
-            const uint32_t dst = smem_u32(sA0 + (size_t)slot * nch * kHaloPitch);
+            const int ty0 = tyi * rows - 1, tx0 = txi * kTileW - 1;
+            const uint32_t dst = smem_u32(sA0 + (size_t)slot * nch * p.halo_pitch);
             const uint4* img = reinterpret_cast<const uint4*>(p.x + (size_t)b * p.Hin * p.Win * p.Cin);
             const uint4* org = img + ((size_t)(tyi * sy_step) * p.Win + txi * sx_step) * nch;
             // asynchronous 16-byte copies (zero fill outside the image); nothing is waited for here, so the loads of
-            // up to `stages` tiles are in flight per CTA
+            // up to `stages` tiles are in flight per CTA.  Tiles whose halo lies inside the image (the large majority at
+            // the resolutions that dominate the run time) skip the per-chunk border logic.
+            const bool interior = ty0 >= 0 && tx0 >= 0 && ty0 + rows + 2 <= p.H && tx0 + kTileW + 2 <= p.W;
+            if (p.ablate & 1) {
+            } else if (interior) {
 #pragma unroll
-            for (int k = 0; k < kItemRegs; ++k) {
-                if (dsto[k] != 0xFFFFFFFFu) {
-                    const int iy = ty0 + (int)(dsto[k] >> 24), ix = tx0 + (int)((dsto[k] >> 16) & 0xFF);
-                    const bool ok = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
-                    cp_async16(dst + (dsto[k] & 0xFFFFu) * 16u, ok ? (const void*)(org + rel[k]) : (const void*)img, ok ? 16u : 0u);
+                for (int k = 0; k < kItemRegs; ++k)
+                    if (meta[k] != 0xFFFFFFFFu) cp_async16_full(dst + (meta[k] & 0x1FFFFFu), org + rel[k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < kItemRegs; ++k) {
+                    if (meta[k] != 0xFFFFFFFFu) {
+                        const int iy = ty0 + (int)(meta[k] >> 25), ix = tx0 + (int)((meta[k] >> 21) & 0xF);
+                        const bool ok = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+                        cp_async16(dst + (meta[k] & 0x1FFFFFu), ok ? (const void*)(org + rel[k]) : (const void*)img, ok ? 16u : 0u);
+                    }
                 }
             }
             for (int i = pt + kItemRegs * 128; i < items; i += 128) {
@@ -148,7 +182,7 @@ k_conv3x3(const ConvParams p) {
                 const int iy = ty0 + hy, ix = tx0 + hx;
                 const bool ok = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
                 const int sy = p.upsample ? (iy >> 1) : iy, sx = p.upsample ? (ix >> 1) : ix;
-                cp_async16(dst + (uint32_t)(c * kHaloPitch + pos) * 16u,
+                cp_async16(dst + (uint32_t)(c * p.halo_pitch + pos) * 16u,
                            ok ? (const void*)(img + ((size_t)sy * p.Win + sx) * nch + c) : (const void*)img, ok ? 16u : 0u);
             }
             cp_async_arrive(&full_a[slot]);
@@ -160,9 +194,11 @@ k_conv3x3(const ConvParams p) {
         //   A: slot base + tap offset (ky*10 + kx positions) + k-step * 2 * kHaloPitch      (16-byte units)
         //   B: weights are packed [tap][k chunk][n] -> the descriptor simply advances by 2*nt per MMA
         const uint32_t idesc = instr_desc_bf16(nt, false, false);
-        const uint64_t a_desc0 = smem_desc(smem_u32(sA0), kHaloPitch * 16u, kHaloW * 16u);
+        const uint64_t a_desc0 = smem_desc(smem_u32(sA0), (uint32_t)p.halo_pitch * 16u, kHaloW * 16u);
         const uint64_t b_desc0 = smem_desc(smem_u32(sW), (uint32_t)nt * 16u, 128u);
-        const uint32_t slot_units = (uint32_t)(nch * kHaloPitch), b_step = (uint32_t)(2 * nt);
+        const uint64_t ones_desc = smem_desc(smem_u32(sOnes), 128u * 16u, 128u);
+        const uint32_t slot_units = (uint32_t)(nch * p.halo_pitch), b_step = (uint32_t)(2 * nt);
+        const uint32_t a_kstep = 2u * (uint32_t)p.halo_pitch;
         const int ksteps = nch >> 1;
         mbar_wait(w_full, 0);
         int slot = 0, acc = 0; uint32_t ph = 0, aph = 0;
@@ -172,26 +208,32 @@ k_conv3x3(const ConvParams p) {
             if (p.consumer_fence) fence_proxy_async();      // (debug switch) cp.async-written operands -> async proxy
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t d = tmem_base + acc * acc_stride;
-                const uint64_t da_slot = a_desc0 + (uint64_t)(slot * slot_units);
-                uint64_t db = b_desc0;
-                uint32_t accum = 0;
+                for (int blk = 0; blk < p.mb; ++blk) {
+                    const uint32_t d = tmem_base + acc * acc_stride + blk * p.blk_stride;
+                    const uint64_t da_blk = a_desc0 + (uint64_t)(slot * slot_units + blk * (kTileH * kHaloW));
+                    uint64_t db = b_desc0;
+                    uint32_t accum = 0;
+                    if (!(p.ablate & 2))
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
-                    uint64_t da = da_slot + (uint64_t)((tap / 3) * kHaloW + (tap % 3));
-                    for (int kk = 0; kk < ksteps; ++kk) {
-                        mma_bf16(d, da, db, idesc, accum);
-                        accum = 1;
-                        da += 2 * kHaloPitch;
-                        db += b_step;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        uint64_t da = da_blk + (uint64_t)((tap / 3) * kHaloW + (tap % 3));
+                        for (int kk = 0; kk < ksteps; ++kk) {
+                            mma_bf16(d, da, db, idesc, accum);
+                            accum = 1;
+                            da += a_kstep;
+                            db += b_step;
+                        }
                     }
+                    if (kBA) mma_bf16(d, ones_desc, db, idesc, 1u);      // + bias (db now points at the bias pseudo-tap)
                 }
+                // ONE commit per tile: the same mbarrier tells the producers that the halo slot is free again and the
+                // epilogue warps that the accumulator is complete (a second tcgen05.commit per tile costs as much
+                // tensor-pipe time as four of these small MMAs)
                 mma_commit(&empty_a[slot]);
-                mma_commit(&tmem_full[acc]);
             }
             __syncwarp();
             if (++slot == p.stages) { slot = 0; ph ^= 1u; }
-            if (++acc == 2) { acc = 0; aph ^= 1u; }
+            if (++acc == p.n_acc) { acc = 0; aph ^= 1u; }
         }
     } else {
         // ================= epilogue: 8 warps; warp = (half << 2) | quarter =================
@@ -203,67 +245,90 @@ k_conv3x3(const ConvParams p) {
         const bool split = kEpiWarps == 8;
         const int u0 = (!split || half == 0) ? 0 : (units + 1) >> 1, u1 = !split ? units : (half == 0 ? (units + 1) >> 1 : units);
         const float inv_c = 1.0f / (float)nt;
-        int acc = 0; uint32_t aph = 0;
+        int acc = 0, slot = 0; uint32_t aph = 0, ph = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const int b = fast_div(tile, p.div_img);
             const int tr = tile - b * p.tiles_per_img;
             const int tyi = fast_div(tr, p.div_tx), txi = tr - tyi * p.tiles_x;
-            const int oy = tyi * kTileH + ry, ox = txi * kTileW + rx;
-            const bool valid = oy < p.H && ox < p.W;
-            mbar_wait(&tmem_full[acc], aph);
+            const int ox = txi * kTileW + rx;
+            mbar_wait(&empty_a[slot], ph);            // k-th completion of this slot's barrier == MMAs of this step done
             tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(quarter * 32) << 16);
-            float scale = 1.0f;
-            if (p.pixelnorm) {
-                float ss = 0.0f;
-                for (int u = u0; u < u1; ++u) {
+            // the accumulators go back to the MMA warp as soon as their last columns sit in registers, before the
+            // arithmetic and the stores of those columns
+            bool released = false;
+            auto release = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);      // one arrival per epilogue warp
+                released = true;
+            };
+            if (!(p.ablate & 4))
+            for (int blk = 0; blk < p.mb; ++blk) {
+                const int oy = (tyi * p.mb + blk) * kTileH + ry;
+                const bool valid = oy < p.H && ox < p.W;
+                const bool last_blk = blk + 1 == p.mb;
+                const uint32_t taddr = tmem_base + acc * acc_stride + blk * p.blk_stride + ((uint32_t)(quarter * 32) << 16);
+                float scale = 1.0f;
+                if (kPN) {
+                    float ss = 0.0f;
+                    for (int u = u0; u < u1; ++u) {
+                        float v[16];
+                        tmem_ld16(taddr + u * 16, v);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float t = kBA ? fmaxf(v[j], p.slope * v[j]) : v[j];
+                            ss = fmaf(t, t, ss);
+                        }
+                    }
+                    float tot = ss;
+                    if (split) {
+                        sPart[half * 128 + m] = ss;
+                        named_bar_sync(1 + quarter, 64);              // the two warps that share this TMEM lane quarter
+                        tot = sPart[m] + sPart[128 + m];
+                        named_bar_sync(1 + quarter, 64);              // sPart may be overwritten by the next block
+                    }
+                    scale = 1.0f / sqrtf(tot * inv_c + 1e-8f);
+                    if (valid && half == 0 && p.inv_norm) p.inv_norm[((size_t)b * p.H + oy) * p.W + ox] = scale;
+                }
+                __nv_bfloat16* dst = p.y + (((size_t)b * p.H + oy) * p.W + ox) * p.Cout + n0;
+                // 16 channels: activation, PixelNorm scale, bf16 pack, two 16-byte stores
+                auto finish16 = [&](const float* v, int u) {
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float t0 = v[2 * j], t1 = v[2 * j + 1];
+                        if (kBA) { t0 = fmaxf(t0, p.slope * t0); t1 = fmaxf(t1, p.slope * t1); }
+                        if (kPN) { t0 *= scale; t1 *= scale; }
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(t0, t1);
+                        pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    if (valid && !((p.ablate & 8) && pk[0] == 0x12345678u)) {
+                        uint4* d4 = reinterpret_cast<uint4*>(dst + u * 16);
+                        d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                };
+                int u = u0;
+                for (; u + 2 <= u1; u += 2) {
+                    float v[32];
+                    tmem_ld16(taddr + u * 16, v);
+                    tmem_ld16(taddr + u * 16 + 16, v + 16);
+                    tmem_wait_ld();
+                    if (last_blk && u + 2 == u1) release();
+                    if (!(p.ablate & 16)) { finish16(v, u); finish16(v + 16, u + 1); }
+                }
+                if (u < u1) {
                     float v[16];
                     tmem_ld16(taddr + u * 16, v);
                     tmem_wait_ld();
-                    const float4* b4 = reinterpret_cast<const float4*>(sBias + u * 16);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 bb = b4[j];
-                        float t0 = v[4 * j] + bb.x, t1 = v[4 * j + 1] + bb.y, t2 = v[4 * j + 2] + bb.z, t3 = v[4 * j + 3] + bb.w;
-                        if (p.lrelu) { t0 = fmaxf(t0, 0.2f * t0); t1 = fmaxf(t1, 0.2f * t1); t2 = fmaxf(t2, 0.2f * t2); t3 = fmaxf(t3, 0.2f * t3); }
-                        ss = fmaf(t0, t0, ss); ss = fmaf(t1, t1, ss); ss = fmaf(t2, t2, ss); ss = fmaf(t3, t3, ss);
-                    }
-                }
-                float tot = ss;
-                if (split) {
-                    sPart[half * 128 + m] = ss;
-                    named_bar_sync(1 + quarter, 64);              // the two warps that share this TMEM lane quarter
-                    tot = sPart[m] + sPart[128 + m];
-                    named_bar_sync(1 + quarter, 64);              // sPart may be overwritten by the next tile
-                }
-                scale = 1.0f / sqrtf(tot * inv_c + 1e-8f);
-                if (valid && half == 0 && p.inv_norm) p.inv_norm[((size_t)b * p.H + oy) * p.W + ox] = scale;
-            }
-            __nv_bfloat16* dst = p.y + (((size_t)b * p.H + oy) * p.W + ox) * p.Cout + n0;
-            for (int u = u0; u < u1; ++u) {
-                float v[16];
-                tmem_ld16(taddr + u * 16, v);
-                tmem_wait_ld();
-                const float4* b4 = reinterpret_cast<const float4*>(sBias + u * 16);
-                uint32_t pk[8];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 bb = b4[j];
-                    float t0 = v[4 * j] + bb.x, t1 = v[4 * j + 1] + bb.y, t2 = v[4 * j + 2] + bb.z, t3 = v[4 * j + 3] + bb.w;
-                    if (p.lrelu) { t0 = fmaxf(t0, 0.2f * t0); t1 = fmaxf(t1, 0.2f * t1); t2 = fmaxf(t2, 0.2f * t2); t3 = fmaxf(t3, 0.2f * t3); }
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(t0 * scale, t1 * scale), h1 = __floats2bfloat162_rn(t2 * scale, t3 * scale);
-                    pk[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
-                    pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
-                }
-                if (valid) {
-                    uint4* d4 = reinterpret_cast<uint4*>(dst + u * 16);
-                    d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    if (last_blk) release();
+                    if (!(p.ablate & 16)) finish16(v, u);
                 }
             }
-            tc_fence_before();
-            mbar_arrive(&tmem_empty[acc]);
-            if (++acc == 2) { acc = 0; aph ^= 1u; }
+            if (!released) release();                 // a warp of the second half without columns of its own (Nt = 16)
+            if (++acc == p.n_acc) { acc = 0; aph ^= 1u; }
+            if (++slot == p.stages) { slot = 0; ph ^= 1u; }
         }
     }
     tc_fence_before();
@@ -309,43 +374,60 @@ __global__ void k_pack_weights(const float* __restrict__ w, int Cout, int Cin, i
     }
 }
 
-struct ConvPlan { int Nt, stages, tmem_cols, n_slices, occupancy, epi_warps; size_t smem; };
+struct ConvPlan { int Nt, stages, tmem_cols, n_slices, occupancy, epi_warps, n_acc, acc_stride, mb, blk_stride, halo_pos, halo_pitch; size_t smem; };
 
-static ConvPlan plan_conv(int Cin, int Cout, bool need_full_n) {
+static ConvPlan plan_conv(int Cin, int Cout, bool need_full_n, int H = 0) {
     const size_t budget = 200 * 1024;
     const int nch = Cin / 8;
     ConvPlan pl{};
-    for (int stages = 2; stages >= 1; --stages) {
-        const size_t halo = (size_t)stages * nch * kHaloPitch * 16;
-        for (int Nt = Cout; Nt >= 16; Nt -= 16) {
-            const size_t wbytes = (size_t)9 * nch * Nt * 16;
-            size_t tot = wbytes + halo + (size_t)(Nt + 8) * 4 + 1024 + 320;      // + PixelNorm partials + barriers
-            if (tot <= budget) {
-                const size_t stage_b = (size_t)nch * kHaloPitch * 16;
-                int cols_ = 32; while (cols_ < 2 * Nt) cols_ <<= 1;
-                // two CTAs per SM hide the latency of the (few, specialised) warps: take that shape when >= 4 halo slots
-                // still fit in half of the shared memory and the TMEM columns of both fit
-                // Several CTAs per SM hide the latency of the (few, specialised) warps.  Registers (72/thread) allow
-                // 3 CTAs of 9 warps (4 epilogue warps) or 2 CTAs of 13 warps (8 epilogue warps); shared memory must hold
-                // >= 4 halo slots per CTA and the TMEM columns of all resident CTAs must fit in 512.
-                static const int force_occ = getenv("MG_CONV_OCC") ? atoi(getenv("MG_CONV_OCC")) : 0;
-                const size_t base = tot - halo;
-                pl.occupancy = 1; pl.epi_warps = 8;
-                size_t cap = budget;
-                if ((force_occ == 0 || force_occ == 3) && cols_ <= 128 && base + 4 * stage_b <= 73 * 1024) { pl.occupancy = 3; pl.epi_warps = 4; cap = 73 * 1024; }
-                else if ((force_occ == 0 || force_occ >= 2) && cols_ <= 256 && base + 4 * stage_b <= 110 * 1024) { pl.occupancy = 2; cap = 110 * 1024; }
-                if (pl.occupancy > 1) { tot = base + 4 * stage_b; stages = 4; }
-                while (stages < kMaxStages && tot + stage_b <= cap) { ++stages; tot += stage_b; }
-                pl.Nt = Nt; pl.stages = stages; pl.smem = tot;
-                pl.n_slices = (Cout + Nt - 1) / Nt;
-                int cols = 32; while (cols < 2 * Nt) cols <<= 1;
-                pl.tmem_cols = cols;
-                if (need_full_n && Nt != Cout) { pl.Nt = 0; }
-                return pl;
-            }
+    // 1. N slice: the widest slice whose resident weights leave room for two single-block halo slots (one if need be).
+    //    The packed weight layout depends on this choice only, never on the shape chosen in step 2.
+    int Nt = 0;
+    for (int stages = 2; stages >= 1 && !Nt; --stages)
+        for (int n = Cout; n >= 16; n -= 16)
+            if ((size_t)9 * nch * n * 16 + (size_t)stages * nch * kHaloPitch * 16 + (size_t)2 * n * 16 + 4096 + 1024 + 384 <= budget) { Nt = n; break; }
+    if (!Nt || (need_full_n && Nt != Cout)) return pl;
+    const size_t base = (size_t)9 * nch * Nt * 16 + (size_t)2 * Nt * 16 + 4096 + 1024 + 384;   // weights, bias pseudo-tap, constant A tile, PixelNorm partials, barriers
+    // 2. shape of one pipeline step.  The warps of a CTA are few and specialised, so (a) several CTAs share an SM
+    //    (registers: 72/thread -> 3 CTAs of 9 warps with 4 epilogue warps, or 2 CTAs of 13 warps with 8) and (b) on
+    //    the large images a step covers `mb` vertically stacked 16 x 8 blocks, which divides the per-step costs
+    //    (barrier round trips, tile index arithmetic, commit) by mb and shrinks the halo overhead.  Requirements: the
+    //    per-thread chunk table of the producers stays in registers, >= 3 halo slots, >= 2 accumulators, and the
+    //    TMEM columns of all resident CTAs fit in 512.
+    static const int force_occ = getenv("MG_CONV_OCC") ? atoi(getenv("MG_CONV_OCC")) : 0;
+    static const int force_mb = getenv("MG_CONV_MB") ? atoi(getenv("MG_CONV_MB")) : 0;
+    static const int force_acc = getenv("MG_CONV_ACC") ? atoi(getenv("MG_CONV_ACC")) : 0;
+    static const int prefs[8][2] = {{2, 4}, {1, 4}, {2, 3}, {1, 3}, {4, 2}, {2, 2}, {1, 2}, {1, 1}};
+    for (int pass = 0; pass < 2; ++pass) {            // pass 1 ignores the debug overrides if they leave no candidate
+        for (const auto& c : prefs) {
+            const int mb = c[0], occ = c[1];
+            if (pass == 0 && ((force_occ && occ != force_occ) || (force_mb && mb != force_mb))) continue;
+            if (mb > 1 && H < kTileH * mb) continue;
+            const int halo_pos = (kTileH * mb + 2) * kHaloW, pitch = halo_pos + 6;
+            if (mb > 1 && halo_pos * nch > 12 * 128) continue;
+            if (occ == 4 && halo_pos * nch > 6 * 128) continue;
+            const size_t stage_b = (size_t)nch * pitch * 16;
+            const size_t cap = occ == 4 ? 54 * 1024 : occ == 3 ? 73 * 1024 : occ == 2 ? 110 * 1024 : budget;
+            const int cols_cap = occ >= 3 ? 128 : occ == 2 ? 256 : 512;
+            const int blk_stride = (Nt + 31) & ~31, acc_stride = mb * blk_stride;
+            const int min_stages = occ > 1 ? ((mb > 1 || occ == 4) ? 3 : 4) : 1;
+            if (occ > 1 && 2 * acc_stride > cols_cap) continue;
+            if (acc_stride > cols_cap || base + min_stages * stage_b > cap) continue;
+            int stages = min_stages;
+            size_t tot = base + stages * stage_b;
+            while (stages < kMaxStages && tot + stage_b <= cap) { ++stages; tot += stage_b; }
+            int n_acc = cols_cap / acc_stride;
+            n_acc = n_acc > kMaxAcc ? kMaxAcc : n_acc;
+            if (n_acc > stages) n_acc = stages;           // the shared slot barrier must not lap the epilogue (see kernel)
+            if (force_acc >= 1 && force_acc <= n_acc) n_acc = force_acc;
+            int cols = 32; while (cols < n_acc * acc_stride) cols <<= 1;
+            pl.Nt = Nt; pl.stages = stages; pl.smem = tot; pl.n_slices = (Cout + Nt - 1) / Nt;
+            pl.occupancy = occ; pl.epi_warps = occ >= 3 ? 4 : 8;
+            pl.mb = mb; pl.blk_stride = blk_stride; pl.acc_stride = acc_stride; pl.n_acc = n_acc; pl.tmem_cols = cols;
+            pl.halo_pos = halo_pos; pl.halo_pitch = pitch;
+            return pl;
         }
     }
-    pl.Nt = 0;
     return pl;
 }
 
@@ -384,7 +466,7 @@ int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* 
     if (ups && ((H | W) & 1)) return MG_ERR_BAD_ARG;
     if (ws_bytes < mg_conv3x3_workspace_bytes(Cin, Cout)) return MG_ERR_WORKSPACE;
     const bool pn = (flags & 2) != 0;
-    ConvPlan pl = plan_conv(Cin, Cout, pn);
+    ConvPlan pl = plan_conv(Cin, Cout, pn, H);
     if (pl.Nt == 0) return MG_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     if (w_f32) {
@@ -399,22 +481,31 @@ int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* 
     p.x = (const __nv_bfloat16*)x; p.wpack = (const uint4*)ws; p.bias = bias; p.y = (__nv_bfloat16*)y; p.inv_norm = inv_norm;
     p.B = B; p.H = H; p.W = W; p.Hin = ups ? H / 2 : H; p.Win = ups ? W / 2 : W; p.Cin = Cin; p.Cout = Cout;
     p.upsample = ups; p.lrelu = flags & 1; p.pixelnorm = pn;
-    p.tiles_x = (W + kTileW - 1) / kTileW; p.tiles_y = (H + kTileH - 1) / kTileH; p.n_tiles = B * p.tiles_x * p.tiles_y;
+    p.tiles_x = (W + kTileW - 1) / kTileW; p.tiles_y = (H + kTileH * pl.mb - 1) / (kTileH * pl.mb); p.n_tiles = B * p.tiles_x * p.tiles_y;
     p.Nt = pl.Nt; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols; p.epi_warps = pl.epi_warps;
+    p.n_acc = pl.n_acc; p.acc_stride = pl.acc_stride; p.mb = pl.mb; p.blk_stride = pl.blk_stride;
+    p.halo_pos = pl.halo_pos; p.halo_pitch = pl.halo_pitch;
     p.idiv = make_item_div(Cin / 8);
     p.consumer_fence = getenv("MG_CONSUMER_FENCE") ? 1 : 0;
+    p.ablate = getenv("MG_CONV_ABLATE") ? atoi(getenv("MG_CONV_ABLATE")) : 0;
     p.tiles_per_img = p.tiles_x * p.tiles_y;
     p.div_img = make_fast_div(p.tiles_per_img);
     p.div_tx = make_fast_div(p.tiles_x);
     if (p.n_tiles >= (1 << 20)) return MG_ERR_UNSUPPORTED;
     static int sm_count = 0;
     if (!sm_count) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
-    cudaFuncSetAttribute(k_conv3x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-    const int ctas = sm_count * pl.occupancy;
+    p.slope = (flags & 1) ? 0.2f : 1.0f;
+    const bool ba = bias != nullptr || (flags & 1);
+    const bool o4 = pl.occupancy == 4;
+    auto kern = o4 ? (pn ? (ba ? k_conv3x3<true, true, true> : k_conv3x3<true, false, true>) : (ba ? k_conv3x3<false, true, true> : k_conv3x3<false, false, true>))
+                   : (pn ? (ba ? k_conv3x3<true, true, false> : k_conv3x3<true, false, false>) : (ba ? k_conv3x3<false, true, false> : k_conv3x3<false, false, false>));
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    int ctas = sm_count * pl.occupancy;
+    if (const char* e = getenv("MG_CONV_MAX_CTAS")) { const int m = atoi(e); if (m > 0 && m < ctas) ctas = m; }   // tests: many steps per CTA
     const int per_slice = max(1, min(p.n_tiles, ctas / pl.n_slices > 0 ? ctas / pl.n_slices : 1));
     {
         ProfScope ps(dgrad ? "k_conv3x3_dgrad" : "k_conv3x3_fprop", st);
-        k_conv3x3<<<dim3(per_slice, pl.n_slices), (pl.epi_warps + 5) * 32, pl.smem, st>>>(p);
+        kern<<<dim3(per_slice, pl.n_slices), (pl.epi_warps + 5) * 32, pl.smem, st>>>(p);
     }
     return check_launch("k_conv3x3");
 }

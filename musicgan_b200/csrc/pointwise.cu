@@ -15,6 +15,62 @@
 #include <cuda_bf16.h>
 
 namespace mg {
+// Per-channel sums over pixels, in two deterministic steps and without atomics.  (Every block ending with C global
+// atomics on the same cache line serialises in one L2 slice: ~27 cycles per warp request, 10-20 us for a few hundred
+// blocks -- more than the streaming time of most layers.)
+//   step 1 (inside the streaming kernel): a thread owns one 8-channel chunk for all its pixels (the grid stride is a
+//           multiple of C/8); the block transposes its 256 x 8 register partials through shared memory and writes ONE
+//           row part[blockIdx.x][C];
+//   step 2 (k_colsum_reduce): gb[c] = sum over rows, fixed order, gb overwritten (no zero fill needed).
+__device__ __forceinline__ void block_colsum_to_row(const float (&acc)[8], float* s_t, float* __restrict__ row,
+                                                    int64_t first, int C8) {
+    // s_t [256][9]: thread-major, padded
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_t[threadIdx.x * 9 + j] = acc[j];
+    __syncthreads();
+    const int C = C8 * 8;
+    const int q0 = (int)((first - threadIdx.x) % C8);      // chunk of thread 0 of this block
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int q = c >> 3, j = c & 7;
+        int t = q - q0; if (t < 0) t += C8;                 // first thread of the block that owns chunk q
+        float v = 0.0f;
+        for (; t < (int)blockDim.x; t += C8) v += s_t[t * 9 + j];
+        row[c] = v;
+    }
+}
+
+// gb[c] = sum_r part[r][c]; block = 8 warps x 32 consecutive channels, warp w takes rows w, w+8, ...
+__global__ void __launch_bounds__(256)
+k_colsum_reduce(const float* __restrict__ part, float* __restrict__ gb, int C, int rows) {
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    float s0 = 0.0f, s1 = 0.0f;
+    if (c < C) {
+        int r = w;
+        for (; r + 8 < rows; r += 16) { s0 += part[(size_t)r * C + c]; s1 += part[(size_t)(r + 8) * C + c]; }
+        if (r < rows) s0 += part[(size_t)r * C + c];
+    }
+    red[w][lane] = s0 + s1;
+    __syncthreads();
+    if (w == 0 && c < C) {
+        float v = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v += red[k][lane];
+        gb[c] = v;
+    }
+}
+
+static const int kColsumMaxBlocks = 148 * 8 + 32;
+
+// grid of a column-sum kernel: blocks * 256 a multiple of C8 so that a thread always meets the same 8-channel chunk
+static unsigned colsum_blocks(int64_t total, int C8) {
+    int64_t blocks = (total + 1023) / 1024;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    while ((blocks * 256) % C8) ++blocks;
+    return (unsigned)blocks;
+}
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.0f ? v : 0.2f * v; }
 
@@ -183,7 +239,7 @@ k_unpool2(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
 // 8-channel chunk for all its pixels (grid stride is a multiple of C/8), so its 8 partial sums stay in registers.
 __global__ void __launch_bounds__(256)
 k_lrelu_bwd(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ gz,
-            float* __restrict__ gb, int C8, int64_t total, int64_t stride) {
+            float* __restrict__ part, int C8, int64_t total, int64_t stride) {
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
@@ -224,17 +280,9 @@ k_lrelu_bwd(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restric
         }
         reinterpret_cast<uint4*>(gz)[i] = o.u;
     }
-    if (gb) {       // block-level reduction in shared memory, then one global atomic per channel per block
-        extern __shared__ float s_gb[];
-        for (int i = threadIdx.x; i < C8 * 8; i += blockDim.x) s_gb[i] = 0.0f;
-        __syncthreads();
-        if (first < total) {
-            const int c0 = (int)(first % C8) * 8;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) atomicAdd(&s_gb[c0 + j], acc[j]);
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < C8 * 8; i += blockDim.x) atomicAdd(&gb[i], s_gb[i]);
+    if (part) {     // this block's row of per-channel sums (k_colsum_reduce adds the rows)
+        __shared__ float s_t[256 * 9];
+        block_colsum_to_row(acc, s_t, part + (size_t)blockIdx.x * C8 * 8, first, C8);
     }
 }
 
@@ -244,7 +292,7 @@ k_lrelu_bwd(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restric
 // one thread per pixel (channels contiguous in NHWC), two passes over its C channels
 __global__ void __launch_bounds__(256)
 k_pixelnorm_lrelu_bwd(const __nv_bfloat16* __restrict__ go, const __nv_bfloat16* __restrict__ o, const float* __restrict__ inv,
-                      __nv_bfloat16* __restrict__ gz, float* __restrict__ gb, int C, int64_t n_pixels) {
+                      __nv_bfloat16* __restrict__ gz, int C, int64_t n_pixels) {
     const int C8 = C >> 3;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pixels; p += (int64_t)gridDim.x * blockDim.x) {
         const uint4* g4 = reinterpret_cast<const uint4*>(go + p * C);
@@ -275,10 +323,11 @@ k_pixelnorm_lrelu_bwd(const __nv_bfloat16* __restrict__ go, const __nv_bfloat16*
     }
 }
 
-// gb[c] += sum over pixels of g[.,c]  (bf16 NHWC); same thread <-> channel-chunk ownership as k_lrelu_bwd
+// part[blockIdx.x][c] = this block's sum over its pixels of g[.,c]  (bf16 NHWC); same thread <-> channel-chunk ownership
+// as k_lrelu_bwd
 __global__ void __launch_bounds__(256)
-k_colsum(const __nv_bfloat16* __restrict__ g, float* __restrict__ gb, int C8, int64_t total, int64_t stride) {
-    extern __shared__ float s_gb[];
+k_colsum(const __nv_bfloat16* __restrict__ g, float* __restrict__ part, int C8, int64_t total, int64_t stride) {
+    __shared__ float s_t[256 * 9];
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
@@ -288,15 +337,7 @@ k_colsum(const __nv_bfloat16* __restrict__ g, float* __restrict__ gb, int C8, in
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(v.h[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
     }
-    for (int i = threadIdx.x; i < C8 * 8; i += blockDim.x) s_gb[i] = 0.0f;
-    __syncthreads();
-    if (first < total) {
-        const int c0 = (int)(first % C8) * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(&s_gb[c0 + j], acc[j]);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < C8 * 8; i += blockDim.x) atomicAdd(&gb[i], s_gb[i]);
+    block_colsum_to_row(acc, s_t, part + (size_t)blockIdx.x * C8 * 8, first, C8);
 }
 
 static unsigned grid_for(int64_t items, int per_block = 256, int cap = 148 * 16) {
@@ -337,40 +378,52 @@ int mg_rgb_wgrad_bf16(const void* g, const void* mask_src, const float* x, float
     const int64_t total = (int64_t)B * HW;
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope ps("k_rgb_wgrad", st);
-    const unsigned gx = grid_for(total, 256 * 8, 148 * 4);
+    const unsigned gx = grid_for(total, 256 * 8, 148 * 2);      // every block ends with 24 same-address atomics: keep the tail short
     k_rgb_wgrad<<<dim3(gx, C / 8), 256, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)mask_src, x, gw, gb, HW, C, total);
     return check_launch("k_rgb_wgrad");
 }
 
-int mg_lrelu_bwd_bf16(const void* gy, const void* y, void* gz, float* gb, int64_t n_pixels, int C, mgStream stream) {
+size_t mg_colsum_workspace_bytes(int C) {
+    return C > 0 ? align_up((size_t)kColsumMaxBlocks * C * sizeof(float), 256) : 0;
+}
+
+// gb (optional, OVERWRITTEN) needs `ws` of mg_colsum_workspace_bytes(C)
+int mg_lrelu_bwd_bf16(const void* gy, const void* y, void* gz, float* gb, void* ws, size_t ws_bytes, int64_t n_pixels, int C, mgStream stream) {
     if (!gy || !y || !gz || n_pixels <= 0 || C < 8 || (C & 7)) return MG_ERR_BAD_ARG;
+    if (gb && (!ws || ws_bytes < mg_colsum_workspace_bytes(C))) return MG_ERR_WORKSPACE;
     const int C8 = C / 8;
     const int64_t total = n_pixels * C8;
     cudaStream_t st = (cudaStream_t)stream;
-    ProfScope ps("k_lrelu_bwd", st);
-    // stride = blocks * 256 must be a multiple of C8 so that a thread always meets the same channel chunk
-    int64_t blocks = (total + 1023) / 1024;
-    if (blocks < 1) blocks = 1;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    while ((blocks * 256) % C8) ++blocks;
-    k_lrelu_bwd<<<(unsigned)blocks, 256, (size_t)C * sizeof(float), st>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y, (__nv_bfloat16*)gz, gb, C8, total, blocks * 256);
+    const unsigned blocks = colsum_blocks(total, C8);
+    {
+        ProfScope ps("k_lrelu_bwd", st);
+        k_lrelu_bwd<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y, (__nv_bfloat16*)gz,
+                                            gb ? (float*)ws : nullptr, C8, total, (int64_t)blocks * 256);
+    }
+    if (gb) {
+        ProfScope ps("k_colsum_reduce", st);
+        k_colsum_reduce<<<(C + 31) / 32, 256, 0, st>>>((const float*)ws, gb, C, (int)blocks);
+    }
     return check_launch("k_lrelu_bwd");
 }
 
-int mg_pixelnorm_lrelu_bwd_bf16(const void* go, const void* o, const float* inv_norm, void* gz, float* gb,
+int mg_pixelnorm_lrelu_bwd_bf16(const void* go, const void* o, const float* inv_norm, void* gz, float* gb, void* ws, size_t ws_bytes,
                                 int64_t n_pixels, int C, mgStream stream) {
     if (!go || !o || !inv_norm || !gz || n_pixels <= 0 || C < 8 || (C & 7) || C > 1024) return MG_ERR_BAD_ARG;
+    if (gb && (!ws || ws_bytes < mg_colsum_workspace_bytes(C))) return MG_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    ProfScope ps("k_pixelnorm_lrelu_bwd", st);
-    k_pixelnorm_lrelu_bwd<<<grid_for(n_pixels, 256, 148 * 8), 256, 0, st>>>(
-        (const __nv_bfloat16*)go, (const __nv_bfloat16*)o, inv_norm, (__nv_bfloat16*)gz, gb, C, n_pixels);
+    {
+        ProfScope ps("k_pixelnorm_lrelu_bwd", st);
+        k_pixelnorm_lrelu_bwd<<<grid_for(n_pixels, 256, 148 * 8), 256, 0, st>>>(
+            (const __nv_bfloat16*)go, (const __nv_bfloat16*)o, inv_norm, (__nv_bfloat16*)gz, C, n_pixels);
+    }
     if (gb) {
         const int C8 = C / 8;
         const int64_t total = n_pixels * C8;
-        int64_t blocks = (total + 255) / 256;
-        if (blocks > 148 * 8) blocks = 148 * 8;
-        while ((blocks * 256) % C8) ++blocks;
-        k_colsum<<<(unsigned)blocks, 256, (size_t)C * sizeof(float), st>>>((const __nv_bfloat16*)gz, gb, C8, total, blocks * 256);
+        const unsigned blocks = colsum_blocks(total, C8);
+        ProfScope ps("k_colsum", st);
+        k_colsum<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)gz, (float*)ws, C8, total, (int64_t)blocks * 256);
+        k_colsum_reduce<<<(C + 31) / 32, 256, 0, st>>>((const float*)ws, gb, C, (int)blocks);
     }
     return check_launch("k_pixelnorm_lrelu_bwd");
 }

@@ -17,7 +17,17 @@ FLAG_LRELU, FLAG_PIXELNORM, FLAG_UPSAMPLE_IN, FLAG_DGRAD = 1, 2, 4, 8
 
 _declared = False
 _ws_cache = {}
-FLOPS = {"count": 0.0}      # conv FLOPs issued through this module (2 * B*H*W * 9*Cin*Cout per call); bench bookkeeping
+# bench bookkeeping of the 3x3 convolution launches issued through this module: FLOPs (2 * B*H*W * 9*Cin*Cout per call),
+# algorithmic HBM bytes (every operand read once, the result written once; weights excluded) and, when "launches" is a
+# list, one (flops, bytes) pair per launch so a per-launch roofline can be summed
+FLOPS = {"count": 0.0, "bytes": 0.0, "launches": None}
+
+
+def _account(flops, nbytes):
+    FLOPS["count"] += flops
+    FLOPS["bytes"] += nbytes
+    if FLOPS["launches"] is not None:
+        FLOPS["launches"].append((flops, nbytes))
 
 
 def _l():
@@ -38,8 +48,10 @@ def _l():
         l.mg_rgb_project_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]
         l.mg_rgb_wgrad_bf16.argtypes = [c_void_p] * 5 + [c_int, c_int64, c_int, c_void_p]
         l.mg_pool2_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
-        l.mg_pixelnorm_lrelu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]
-        l.mg_lrelu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]
+        l.mg_colsum_workspace_bytes.restype = c_size_t
+        l.mg_colsum_workspace_bytes.argtypes = [c_int]
+        l.mg_pixelnorm_lrelu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int64, c_int, c_void_p]
+        l.mg_lrelu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int64, c_int, c_void_p]
         l.mg_conv3x3_pack_weights.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]
         _declared = True
     return l
@@ -125,7 +137,7 @@ def conv3x3(x: th.Tensor, w: th.Tensor, bias=None, *, lrelu=False, pixelnorm=Fal
         ws, w_ptr = _workspace(x.device, l.mg_conv3x3_workspace_bytes(cin, cout)), w.data_ptr()
     if bias is not None:
         assert bias.dtype == th.float32 and bias.numel() == cout and bias.is_cuda
-    FLOPS["count"] += 2.0 * B * H * W * 9 * cin * cout
+    _account(2.0 * B * H * W * 9 * cin * cout, 2.0 * (x.numel() + y.numel()))
     with th.cuda.device(x.device):
         _lib.check(l.mg_conv3x3_bf16(x.data_ptr(), w_ptr, bias.data_ptr() if bias is not None else None,
                                      y.data_ptr(), inv.data_ptr() if inv is not None else None,
@@ -143,7 +155,7 @@ def conv3x3_wgrad(dy: th.Tensor, x: th.Tensor, *, upsample_in=False) -> th.Tenso
     assert x.shape[0] == B and (x.shape[2] * (2 if upsample_in else 1), x.shape[3] * (2 if upsample_in else 1)) == (H, W)
     dw = th.empty((cout, cin, 3, 3), dtype=th.float32, device=dy.device)      # overwritten: no zero fill needed
     l = _l()
-    FLOPS["count"] += 2.0 * B * H * W * 9 * cin * cout
+    _account(2.0 * B * H * W * 9 * cin * cout, 2.0 * (x.numel() + dy.numel()))
     ws = _workspace(dy.device, l.mg_conv3x3_wgrad_workspace_bytes(B, H, W, cin, cout), "wgrad")
     with th.cuda.device(dy.device):
         _lib.check(l.mg_conv3x3_wgrad_bf16(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(),
@@ -236,10 +248,14 @@ def pixelnorm_lrelu_bwd(go: th.Tensor, o: th.Tensor, inv: th.Tensor, want_bias_g
     B, C, H, W = o.shape
     inv = inv.float().contiguous()
     gz = th.empty_like(o)
-    gb = th.zeros((C,), dtype=th.float32, device=o.device) if want_bias_grad else None
+    gb = th.empty((C,), dtype=th.float32, device=o.device) if want_bias_grad else None      # overwritten by the kernel
+    l = _l()
+    ws = _workspace(o.device, l.mg_colsum_workspace_bytes(C), "colsum") if want_bias_grad else None
     with th.cuda.device(o.device):
-        _lib.check(_l().mg_pixelnorm_lrelu_bwd_bf16(go.data_ptr(), o.data_ptr(), inv.data_ptr(), gz.data_ptr(),
-                                                    gb.data_ptr() if gb is not None else None, B * H * W, C, _stream()),
+        _lib.check(l.mg_pixelnorm_lrelu_bwd_bf16(go.data_ptr(), o.data_ptr(), inv.data_ptr(), gz.data_ptr(),
+                                                 gb.data_ptr() if gb is not None else None,
+                                                 ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
+                                                 B * H * W, C, _stream()),
                    "mg_pixelnorm_lrelu_bwd_bf16")
     return gz, gb
 
@@ -250,8 +266,11 @@ def lrelu_bwd(gy: th.Tensor, y: th.Tensor, want_bias_grad: bool = True):
     _check_act(y, "lrelu_bwd y")
     B, C, H, W = y.shape
     gz = th.empty_like(y)
-    gb = th.zeros((C,), dtype=th.float32, device=y.device) if want_bias_grad else None
+    gb = th.empty((C,), dtype=th.float32, device=y.device) if want_bias_grad else None      # overwritten by the kernel
+    l = _l()
+    ws = _workspace(y.device, l.mg_colsum_workspace_bytes(C), "colsum") if want_bias_grad else None
     with th.cuda.device(y.device):
-        _lib.check(_l().mg_lrelu_bwd_bf16(gy.data_ptr(), y.data_ptr(), gz.data_ptr(), gb.data_ptr() if gb is not None else None,
-                                          B * H * W, C, _stream()), "mg_lrelu_bwd_bf16")
+        _lib.check(l.mg_lrelu_bwd_bf16(gy.data_ptr(), y.data_ptr(), gz.data_ptr(), gb.data_ptr() if gb is not None else None,
+                                       ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
+                                       B * H * W, C, _stream()), "mg_lrelu_bwd_bf16")
     return gz, gb

@@ -21,6 +21,7 @@ def _mk(B, C, H, W, seed):
 SHAPES = [  # (B, Cin, Cout, H, W)
     (1, 16, 16, 16, 8), (2, 32, 32, 32, 32), (2, 16, 32, 64, 64), (1, 48, 32, 40, 24), (3, 64, 48, 16, 16),
     (2, 128, 112, 8, 8), (2, 160, 160, 4, 4), (4, 144, 160, 2, 2), (2, 32, 128, 4, 4), (1, 32, 16, 128, 128),
+    (1, 16, 32, 72, 20), (2, 32, 16, 40, 24), (1, 16, 16, 200, 12),      # ragged heights with 4 / 2 stacked blocks per step
 ]
 
 
@@ -37,7 +38,7 @@ def test_fprop(B, Cin, Cout, H, W):
     assert rel_l2(y, ref) <= 4e-3, rel_l2(y, ref)
 
 
-@pytest.mark.parametrize("B,Cin,Cout,H,W", SHAPES[:7])
+@pytest.mark.parametrize("B,Cin,Cout,H,W", SHAPES[:7] + SHAPES[10:])
 def test_dgrad(B, Cin, Cout, H, W):
     from musicgan_b200.networks import ops
     dy = _mk(B, Cout, H, W, 3)
@@ -47,6 +48,42 @@ def test_dgrad(B, Cin, Cout, H, W):
     ref = F.conv_transpose2d(dy.float(), w.bfloat16().float(), padding=1)
     assert dx.shape == ref.shape
     assert rel_l2(dx, ref) <= 4e-3, rel_l2(dx, ref)
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 16, 32, 64, 64), (3, 32, 16, 40, 24), (2, 48, 32, 40, 24), (8, 160, 160, 4, 4),
+                                             (2, 32, 48, 64, 32), (1, 16, 16, 200, 12)])
+def test_ring_wraparound(B, Cin, Cout, H, W, monkeypatch):
+    """Few CTAs -> every CTA walks many pipeline steps, so halo slots, accumulators and their barrier phases wrap
+    around several times (the default grids of these small shapes give each CTA a single step)."""
+    from musicgan_b200.networks import ops
+    monkeypatch.setenv("MG_CONV_MAX_CTAS", "2")
+    x = _mk(B, Cin, H, W, 11)
+    dy = _mk(B, Cout, H, W, 12)
+    g = torch.Generator().manual_seed(13)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    y = ops.conv3x3(x, w, b, lrelu=True)
+    ref = F.leaky_relu(F.conv2d(x.float(), w.bfloat16().float(), b, padding=1), 0.2)
+    assert rel_l2(y, ref) <= 4e-3, rel_l2(y, ref)
+    dx = ops.conv3x3(dy, w, None, dgrad=True)
+    ref = F.conv_transpose2d(dy.float(), w.bfloat16().float(), padding=1)
+    assert rel_l2(dx, ref) <= 4e-3, rel_l2(dx, ref)
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("Cin,Cout", [(16, 32), (64, 112), (160, 160)])
+def test_bias_enters_through_the_accumulator(Cin, Cout):
+    """The bias is added by one extra K = 16 MMA as a bf16 pair hi + lo (conv_igemm.cu): with zero weights the output
+    must be bf16(LeakyReLU(bias)) -- i.e. the pair carries the fp32 bias to well below one bf16 ulp -- in every N slice."""
+    from musicgan_b200.networks import ops
+    x = _mk(2, Cin, 16, 16, 21)
+    w = torch.zeros(Cout, Cin, 3, 3, device="cuda")
+    b = (torch.randn(Cout, generator=torch.Generator().manual_seed(22)) * 3).cuda()
+    y = ops.conv3x3(x, w, b, lrelu=True).float()
+    ref = F.leaky_relu(b, 0.2).view(1, -1, 1, 1).expand_as(y)
+    ulp = ref.abs() * 2.0 ** -8
+    assert ((y - ref).abs() <= ulp).all()                                   # within one bf16 rounding everywhere
+    assert (y == ref.bfloat16().float()).float().mean().item() >= 0.99      # and the correctly rounded value nearly always
 
 
 @pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 32, 32, 16, 16), (1, 48, 32, 32, 16), (2, 128, 128, 4, 4), (2, 32, 16, 64, 64)])

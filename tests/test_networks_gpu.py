@@ -103,9 +103,17 @@ def test_critic_and_generator_step_gradients(golden_dir, name):
     t_gp = _oracle_term_grads(sd_d, lambda d: no.gradient_penalty(d, x_real, x_fake, alpha, stage, eps))
     denom = sum(torch.cat([v.flatten() for v in t.values() if v is not None]).double().norm().item() for t in (t_real, t_fake, t_gp))
     e_terms = (g.double() - r.double()).norm().item() / denom
-    print(f"{name}: critic-step grads: error / (|g_real|+|g_fake|+|g_gp|) = {e_terms:.2e} (plain rel-L2 of the difference {rel(g, r):.2e}); "
+    # noise floor in the same normalisation: the fp32 oracle's own critic gradient when ONLY the weights of G and D are
+    # rounded to bf16 (the penalty term is ill conditioned, see test_gradient_penalty_double_backward)
+    rb = lambda sd: {k: v.bfloat16().float() for k, v in sd.items()}
+    refb = no.d_step(rb(sd_g), rb(sd_d), z, x_real, eps, alpha, stage)
+    keys = [k for k, v in ref["grads"].items() if v is not None]
+    floor = (torch.cat([refb["grads"][k].flatten() for k in keys]).double()
+             - torch.cat([ref["grads"][k].flatten() for k in keys]).double()).norm().item() / denom
+    print(f"{name}: critic-step grads: error / (|g_real|+|g_fake|+|g_gp|) = {e_terms:.2e} (oracle floor under bf16 weight "
+          f"rounding {floor:.2e}; plain rel-L2 of the difference {rel(g, r):.2e}); "
           f"d_loss {d_loss.item():.6f} vs {ref['loss'].item():.6f}; gp {gp.item():.5f} vs {ref['gp'].item():.5f}")
-    assert e_terms <= TOL, e_terms
+    assert e_terms <= max(TOL, 2.5 * floor), (e_terms, floor)        # same factor as the penalty term on its own
     assert abs(gp.item() - float(gold["gp"])) <= 1e-2 * abs(float(gold["gp"]))
     assert rel(out_real, torch.from_numpy(gold["out_real"])) <= TOL
     for p in gen.parameters():
