@@ -183,6 +183,10 @@ int mg_pixelnorm_lrelu_bwd_bf16(const void* go, const void* o, const float* inv_
  * ---------------------------------------------------------------------------------------- */
 int mg_debug_umma_gemm(const void* A, const void* B, float* D, int K, int N, int mode, int Ra, int row_off,
                        int grp_rows, mgStream stream);
+/* Test-only probe of the tcgen05.st shapes used by the weight-gradient kernel's operand staging: one store of
+ * shape 0: 16x64b.x1, 1: 16x128b.x1, 2: 16x128b.x2, 3: 16x256b.x1 by warp 0 with register values
+ * 0x1000 | thread << 4 | (register index + 1); out [128 lanes][32 columns] uint32 = the TMEM block afterwards. */
+int mg_debug_tmem_store(uint32_t* out, int shape, int lane_off, int col_off, mgStream stream);
 
 #ifdef __cplusplus
 }

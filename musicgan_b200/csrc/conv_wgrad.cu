@@ -68,8 +68,8 @@ k_conv3x3_wgrad(const WgradParams p) {
 
     constexpr int kProd0 = kXposeWarps, kMma0 = kXposeWarps + 4;
     if (tid == 0) {
-        for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], kWgradMmaWarps + kXposeWarps * 32); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], kXposeWarps * 32); mbar_init(&a_empty[i], kWgradMmaWarps); }
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], kWgradMmaWarps + kXposeWarps); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], kXposeWarps); mbar_init(&a_empty[i], kWgradMmaWarps); }
         mbar_init(done, kWgradMmaWarps);
         mbar_fence_init();
     }
@@ -157,16 +157,27 @@ k_conv3x3_wgrad(const WgradParams p) {
         const int quarter = warp & 3, khalf = warp >> 2;
         const int L = quarter * 32 + lane;                   // TMEM lane == row within a block
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        // per block: where this lane's row (tap, ci) starts inside a staged x halo (bytes), or -1 if the row is padding
-        int row_off[kMaxBlocks];
+        // A 32-row quarter of a block is two groups of 16 rows = one tap x two 8-channel chunks (Cin is a multiple of
+        // 16).  Per group and pair of tile rows (y, y+1) ONE ldmatrix.x4.trans fetches four 8 x 8 matrices
+        //     (chunk c0, row y) (chunk c0+1, row y) (chunk c0, row y+1) (chunk c0+1, row y+1)
+        // -- 8 pixels x 8 channels each, 128 contiguous bytes of the staged halo -- and hands thread i, per matrix, the
+        // pixel pair 2(i%4), 2(i%4)+1 of channel i/4 packed in one register: exactly the fragment that
+        // tcgen05.st.16x128b.x2 scatters to TMEM lanes i/4 and i/4+8, columns i%4 and 4+i%4 (probed:
+        // mg_debug_tmem_store), i.e. lane = row (tap, ci), column = pixel pair.  Two instructions move 16 rows x 16
+        // pixels; the former per-thread path needed 16 two-byte loads and 8 byte-permutes for ONE row.
+        int goff[kMaxBlocks][2];       // per block and 16-row group: byte offset of (chunk c0, tap) in a staged x halo, or -1 (padding rows)
+        const int lane_part = (((lane >> 3) & 1) * kHaloPitch + (lane >> 4) * kHaloW + (lane & 7)) * 16;
 #pragma unroll
         for (int j = 0; j < kMaxBlocks; ++j) {
-            const int r = (blk0 + j) * 128 + L;
-            row_off[j] = -1;
-            if (j < nb && r < rows_total) {
-                const int tap = fast_div(r, p.div_cin), ci = r - tap * p.Cin;
-                const int ky = tap / 3, kx = tap - ky * 3;
-                row_off[j] = ((ci >> 3) * kHaloPitch + ky * kHaloW + kx) * 16 + (ci & 7) * 2;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const int r0 = (blk0 + j) * 128 + quarter * 32 + g * 16;
+                goff[j][g] = -1;
+                if (j < nb && r0 < rows_total) {
+                    const int tap = fast_div(r0, p.div_cin), ci0 = r0 - tap * p.Cin;
+                    const int ky = tap / 3, kx = tap - ky * 3;
+                    goff[j][g] = ((ci0 >> 3) * kHaloPitch + ky * kHaloW + kx) * 16 + lane_part;
+                }
             }
         }
         int slot = 0, buf = 0; uint32_t ph = 0, aph = 0;
@@ -174,32 +185,30 @@ k_conv3x3_wgrad(const WgradParams p) {
             mbar_wait(&a_empty[buf], aph ^ 1u);
             mbar_wait(&full[slot], ph);
             tc_fence_after();
-            const unsigned char* s_x = stage0 + slot * stage_bytes + dy_bytes;
+            const uint32_t s_x = smem_u32(stage0 + slot * stage_bytes + dy_bytes) + (uint32_t)(khalf * 8 * kHaloW * 16);
 #pragma unroll
             for (int j = 0; j < kMaxBlocks; ++j) {
-                if (j < nb) {
-                    const uint32_t ta = tmem_a + buf * a_cols + j * 64 + khalf * 32 + lane_addr;
-                    const bool ok = row_off[j] >= 0;
-                    const unsigned char* row = s_x + (ok ? row_off[j] : 0);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {            // 8 columns = 16 pixels = tile rows 8*khalf + 2g, +1
-                        uint32_t r[8];
+                for (int g = 0; g < 2; ++g) {
+                    if (goff[j][g] >= 0) {
+                        const uint32_t ta = tmem_a + buf * a_cols + j * 64 + khalf * 32 + lane_addr + ((uint32_t)(g * 16) << 16);
+                        const uint32_t src = s_x + (uint32_t)goff[j][g];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const int ry = khalf * 8 + g * 2 + (c >> 2), rx = (c & 3) * 2;
-                            const unsigned char* e = row + (ry * kHaloW + rx) * 16;
-                            uint32_t lo = 0, hi = 0;
-                            if (ok) { lo = *reinterpret_cast<const uint16_t*>(e); hi = *reinterpret_cast<const uint16_t*>(e + 16); }
-                            r[c] = lo | (hi << 16);
+                        for (int t = 0; t < 4; ++t) {            // tile rows 8*khalf + 2t, +1  ->  columns 8t .. 8t+7
+                            uint32_t r0, r1, r2, r3;
+                            ldmatrix_x4_trans(src + (uint32_t)(t * 2 * kHaloW * 16), r0, r1, r2, r3);
+                            tmem_st_16x128b_x2(ta + t * 8, r0, r1, r2, r3);
                         }
-                        tmem_st8(ta + g * 8, r);
                     }
                 }
             }
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(&a_full[buf]);
-            mbar_arrive(&empty[slot]);       // this thread no longer reads the smem slot (the MMA warps commit theirs)
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&a_full[buf]);
+                mbar_arrive(&empty[slot]);   // this warp no longer reads the smem slot (the MMA warps commit theirs)
+            }
             if (++slot == p.stages) { slot = 0; ph ^= 1u; }
             if (++buf == 2) { buf = 0; aph ^= 1u; }
         }

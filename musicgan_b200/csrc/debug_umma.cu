@@ -108,3 +108,60 @@ extern "C" int mg_debug_umma_gemm(const void* A, const void* B, float* D, int K,
                                                           row_off, grp_rows);
     return check_launch("k_debug_umma");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Probe of the tcgen05.st data-path shapes (which thread register lands in which TMEM lane / column):
+// 128 threads; the TMEM block [128 lanes][32 columns] is zero-filled, warp 0 executes ONE store of the shape under
+// test with register values tag(thread, register index), then every warp dumps its lane quarter with the known
+// 32x32b load.  out[lane][col] (uint32), 0 = untouched.
+//   shape 0: 16x64b.x1 (1 reg)   1: 16x128b.x1 (2 regs)   2: 16x128b.x2 (4 regs)   3: 16x256b.x1 (4 regs)
+//   lane_off / col_off: lane and column fields of the store address
+// ------------------------------------------------------------------------------------------------
+namespace mg {
+__global__ void __launch_bounds__(128)
+k_debug_tmem_store(uint32_t* __restrict__ out, int shape, int lane_off, int col_off) {
+    using namespace umma;
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) tmem_alloc(&slot, 32);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t base = slot;
+    const uint32_t mine = base + ((uint32_t)(warp * 32) << 16);
+    uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < 32; c += 8) tmem_st8(mine + c, z);
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) {
+        const uint32_t a = base + ((uint32_t)lane_off << 16) + (uint32_t)col_off;
+        const uint32_t t = 0x1000u | ((uint32_t)lane << 4);
+        if (shape == 0) asm volatile("tcgen05.st.sync.aligned.16x64b.x1.b32 [%0], {%1};" ::"r"(a), "r"(t | 1u) : "memory");
+        else if (shape == 1) asm volatile("tcgen05.st.sync.aligned.16x128b.x1.b32 [%0], {%1, %2};" ::"r"(a), "r"(t | 1u), "r"(t | 2u) : "memory");
+        else if (shape == 2) asm volatile("tcgen05.st.sync.aligned.16x128b.x2.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(t | 1u), "r"(t | 2u), "r"(t | 3u), "r"(t | 4u) : "memory");
+        else asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(t | 1u), "r"(t | 2u), "r"(t | 3u), "r"(t | 4u) : "memory");
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    for (int c = 0; c < 32; c += 16) {
+        float v[16];
+        tmem_ld16(mine + c, v);
+        tmem_wait_ld();
+        for (int j = 0; j < 16; ++j) out[(warp * 32 + lane) * 32 + c + j] = __float_as_uint(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(base, 32);
+}
+}  // namespace mg
+
+extern "C" int mg_debug_tmem_store(uint32_t* out, int shape, int lane_off, int col_off, mgStream stream) {
+    using namespace mg;
+    if (!out || shape < 0 || shape > 3) return MG_ERR_BAD_ARG;
+    k_debug_tmem_store<<<1, 128, 0, (cudaStream_t)stream>>>(out, shape, lane_off, col_off);
+    return check_launch("k_debug_tmem_store");
+}

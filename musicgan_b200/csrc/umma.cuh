@@ -122,6 +122,17 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
+// thread i, registers (r0, r1, r2, r3) -> TMEM (lane i/4, col i%4), (lane i/4 + 8, col i%4), (lane i/4, col 4 + i%4),
+// (lane i/4 + 8, col 4 + i%4) relative to taddr: the fragment layout of ldmatrix.x4(.trans) / mma.sync operands
+__device__ __forceinline__ void tmem_st_16x128b_x2(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    asm volatile("tcgen05.st.sync.aligned.16x128b.x2.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+// four 8 x 8 b16 matrices (lane l supplies the 16-byte row l%8 of matrix l/8), transposed on the way: thread i receives,
+// per matrix, elements [2(i%4)][i/4] (low half) and [2(i%4)+1][i/4] (high half)
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t saddr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(saddr) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // arrive on `bar` once every previously issued MMA of this thread has completed (implies fence::before_thread_sync)
