@@ -14,6 +14,7 @@ from __future__ import annotations
 import torch as th
 
 from . import networks
+from .train_step import frozen
 from .networks import ops
 
 
@@ -51,11 +52,13 @@ class GraphedSteps:
     def _generator_body(self):
         gen, disc, alpha = self.gen, self.disc, self.alpha
         z = th.randn(self.z_shape, device=self.x_real.device)
-        out_fake = disc(gen(z, alpha), alpha)
-        g_loss = networks.wasserstein_generator_loss(out_fake)
-        # only G's gradients are needed (the reference computes and discards D's, train.py:208-214)
+        # only G's gradients are needed (the reference computes and discards D's, train.py:208-214): with the critic
+        # frozen its weight-gradient kernels are not even launched
         params = [p for p in gen.parameters()]
-        grads = th.autograd.grad(g_loss, params, allow_unused=True)
+        with frozen(disc):
+            out_fake = disc(gen(z, alpha), alpha)
+            g_loss = networks.wasserstein_generator_loss(out_fake)
+            grads = th.autograd.grad(g_loss, params, allow_unused=True)
         for p, g in zip(params, grads):
             p.grad = g
         if self.sync_g is not None:

@@ -28,6 +28,23 @@ def _act(t: th.Tensor) -> th.Tensor:
     return ops.as_act(t)
 
 
+# ctx.needs_input_grad is fixed when the forward runs (does the INPUT require grad?), it does not know which
+# gradients a particular backward call was asked for.  The gradient penalty's inner autograd.grad(out, x_hat,
+# create_graph=True) wants the input gradient only, yet every block would also launch its weight- and bias-gradient
+# kernels (a quarter of all weight-gradient launches of a critic step).  `input_grads_only()` switches them off for
+# the duration of such a call.
+_param_grads = [True]
+
+
+class input_grads_only:
+    def __enter__(self):
+        self.prev, _param_grads[0] = _param_grads[0], False
+
+    def __exit__(self, *exc):
+        _param_grads[0] = self.prev
+        return False
+
+
 class ConvFprop(Function):
     """y = conv3x3(x, w), no bias / activation (linear in x and in w)."""
 
@@ -40,7 +57,7 @@ class ConvFprop(Function):
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         gx = ConvDgrad.apply(gy, w) if ctx.needs_input_grad[0] else None
-        gw = ConvWgrad.apply(gy, x) if ctx.needs_input_grad[1] else None
+        gw = ConvWgrad.apply(gy, x) if ctx.needs_input_grad[1] and _param_grads[0] else None
         return gx, gw
 
 
@@ -56,7 +73,7 @@ class ConvDgrad(Function):
     def backward(ctx, gdx):
         g, w = ctx.saved_tensors
         gg = ConvFprop.apply(gdx, w) if ctx.needs_input_grad[0] else None
-        gw = ConvWgrad.apply(g, gdx) if ctx.needs_input_grad[1] else None
+        gw = ConvWgrad.apply(g, gdx) if ctx.needs_input_grad[1] and _param_grads[0] else None
         return gg, gw
 
 
@@ -100,9 +117,9 @@ class ConvBiasLReLU(Function):
             gz = gy * _lrelu_mask(y)
             gb = gz.float().sum(dim=(0, 2, 3))
         else:
-            gz, gb = LReLUBwd.apply(gy, y)
+            gz, gb = LReLUBwd.apply(gy, y, ctx.needs_input_grad[2] and _param_grads[0])
         gx = ConvDgrad.apply(gz, w) if ctx.needs_input_grad[0] else None
-        gw = ConvWgrad.apply(gz, x) if ctx.needs_input_grad[1] else None
+        gw = ConvWgrad.apply(gz, x) if ctx.needs_input_grad[1] and _param_grads[0] else None
         return gx, gw, (gb if ctx.needs_input_grad[2] else None)
 
 
@@ -111,23 +128,23 @@ class LReLUBwd(Function):
     multiply (plus the broadcast of the bias-gradient cotangent)."""
 
     @staticmethod
-    def forward(ctx, gy, y):
+    def forward(ctx, gy, y, want_bias_grad=True):
         ctx.save_for_backward(y)
         ctx.set_materialize_grads(False)       # an unused bias-gradient output arrives as None, not as zeros
-        gz, gb = ops.lrelu_bwd(gy, y)
+        gz, gb = ops.lrelu_bwd(gy, y, want_bias_grad=bool(want_bias_grad))
         return gz, gb
 
     @staticmethod
     def backward(ctx, ggz, ggb):
         (y,) = ctx.saved_tensors
         if ggz is None and ggb is None:
-            return None, None
+            return None, None, None
         if ggb is None:                        # the usual double-backward case: the same masked multiply, same kernel
-            return LReLUBwd.apply(ggz, y)[0], None
+            return LReLUBwd.apply(ggz, y, False)[0], None, None
         g = ggb.float()[None, :, None, None].expand(y.shape)
         if ggz is not None:
             g = g + ggz.float()
-        return (_act(g) * _lrelu_mask(y)), None
+        return (_act(g) * _lrelu_mask(y)), None, None
 
 
 class GenConv(Function):
@@ -187,7 +204,7 @@ class RgbExpand(Function):
         m = m if ctx.has_mask else None
         gx = RgbProject.apply(gy, w, m) if ctx.needs_input_grad[0] else None
         gw = gb = None
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+        if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and _param_grads[0]:
             gw, gb = RgbWgrad.apply(gy, m, x)
             gw = gw.reshape(ctx.w_shape)
         return gx, gw, gb, None, None
@@ -207,7 +224,7 @@ class RgbProject(Function):
         a, w, m = ctx.saved_tensors
         ga = RgbExpand.apply(gout, w, None, m, False) if ctx.needs_input_grad[0] else None
         gw = None
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and _param_grads[0]:
             gw, _ = RgbWgrad.apply(a, m, gout)
             gw = gw.reshape(ctx.w_shape)
         return ga, gw, None

@@ -215,9 +215,10 @@ class Discriminator(nn.Module):
         if not x_interpolated.requires_grad:
             x_interpolated.requires_grad_(True)
         out_interpolated = self(x_interpolated, alpha)
-        gradients = th.autograd.grad(out_interpolated, x_interpolated,
-                                     grad_outputs=th.ones(out_interpolated.size(), device=x_real.device),
-                                     create_graph=True, retain_graph=True)
+        with fn.input_grads_only():      # this call wants d out / d x_hat only: no weight / bias gradient kernels
+            gradients = th.autograd.grad(out_interpolated, x_interpolated,
+                                         grad_outputs=th.ones(out_interpolated.size(), device=x_real.device),
+                                         create_graph=True, retain_graph=True)
         gradients = gradients[0].reshape(batch_size, -1)
         gradients_norm = gradients.norm(2, dim=1)
         return 10. * ((gradients_norm - 1.) ** 2.).mean()

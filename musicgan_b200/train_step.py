@@ -28,13 +28,32 @@ def critic_step(gen, disc, optim_disc, z, x_real, alpha: float, eps=None, step: 
     return disc_loss.detach(), grad_pen.detach(), out_real.detach(), out_fake.detach()
 
 
+class frozen:
+    """The critic's parameters do not require grad inside the block: the generator step differentiates THROUGH the
+    critic but uses none of its parameter gradients (the reference computes them and throws them away at the next
+    zero_grad, train.py:203-214) -- 18 weight-gradient launches per generator step that are simply not issued here."""
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+
+    def __enter__(self):
+        for p in self.params:
+            p.requires_grad_(False)
+
+    def __exit__(self, *exc):
+        for p in self.params:
+            p.requires_grad_(True)
+        return False
+
+
 def generator_step(gen, disc, optim_gen, z, alpha: float, step: bool = True):
-    x_fake = gen(z, alpha)
-    out_fake = disc(x_fake, alpha)
-    gen_loss = networks.wasserstein_generator_loss(out_fake)
     gen.zero_grad()
     disc.zero_grad()
-    gen_loss.backward()
+    with frozen(disc):
+        x_fake = gen(z, alpha)
+        out_fake = disc(x_fake, alpha)
+        gen_loss = networks.wasserstein_generator_loss(out_fake)
+        gen_loss.backward()
     if step and optim_gen is not None:
         optim_gen.step()
     return gen_loss.detach(), out_fake.detach()
