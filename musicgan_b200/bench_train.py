@@ -47,8 +47,8 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
     stage, batch, alpha = 7, args.batch, 0.5
     gen, disc = _build(stage, 0, dev)
     use_graphs = bool(int(os.environ.get("MG_GRAPHS", "1")))
-    opt_g = th.optim.Adam(gen.parameters(), lr=1e-3, betas=(0.0, 0.9), capturable=use_graphs)
-    opt_d = th.optim.Adam(disc.parameters(), lr=1e-3, betas=(0.0, 0.9), capturable=use_graphs)
+    opt_g = th.optim.Adam(gen.parameters(), lr=1e-3, betas=(0.0, 0.9), capturable=use_graphs, fused=True)
+    opt_d = th.optim.Adam(disc.parameters(), lr=1e-3, betas=(0.0, 0.9), capturable=use_graphs, fused=True)
     th.cuda.manual_seed(1000 + rank)
     g = None
     res = 4 * 2 ** stage

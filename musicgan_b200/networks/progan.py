@@ -104,7 +104,8 @@ class Generator(nn.Module):
         new_mp = self.__end_block(top)
         if self.__last_end_block is None:
             return new_mp
-        return alpha * new_mp + (1. - alpha) * self.__last_end_block(out)
+        # alpha * new + (1 - alpha) * old (generator.py fade-in) as ONE kernel: old + alpha * (new - old)
+        return th.lerp(self.__last_end_block(out), new_mp, alpha)
 
     def next_layer(self) -> bool:
         if not self.growing:
@@ -183,7 +184,7 @@ class Discriminator(nn.Module):
         _require_cuda(x, "Discriminator.forward")
         out = self.__conv_blocks[self.__curr_layer](self.__start_block(x))
         if self.__last_start_block is not None:
-            out = alpha * out + (1 - alpha) * self.__last_start_block(x)
+            out = th.lerp(self.__last_start_block(x), out, alpha)       # alpha * out + (1 - alpha) * old, one kernel, one rounding
         for i in range(self.__curr_layer + 1, len(self.__conv_blocks)):
             out = self.__conv_blocks[i](out)
         return self.__clf(out.flatten(1, -1).float())

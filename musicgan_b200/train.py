@@ -46,8 +46,9 @@ def train(run_name: str, input_dataset_path: str, output_dir: str, *,
         for p in list(gen.parameters()) + list(disc.parameters()):
             dist.broadcast(p.data, src=0)
         th.manual_seed(1000 + rank + (seed or 0))     # per-rank latent / epsilon streams
-    optim_gen = th.optim.Adam(gen.parameters(), lr=gen_lr, betas=betas)
-    optim_disc = th.optim.Adam(disc.parameters(), lr=disc_lr, betas=betas)
+    # fused=True: one multi-tensor update kernel per optimizer step instead of ~100 tiny foreach launches (same fp32 math)
+    optim_gen = th.optim.Adam(gen.parameters(), lr=gen_lr, betas=betas, fused=True)
+    optim_disc = th.optim.Adam(disc.parameters(), lr=disc_lr, betas=betas, fused=True)
     bucket_g, bucket_d = parallel.FlatGradBucket(gen.parameters()), parallel.FlatGradBucket(disc.parameters())
 
     dataset = audio.AudioDataset(input_dataset_path)

@@ -10,8 +10,8 @@ from musicgan_b200.graphed import GraphedSteps
 dev = th.device("cuda", 0)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 gen, disc = bench_train._build(7, 0, dev)
-opt_g = th.optim.Adam(gen.parameters(), lr=1e-3, betas=(0.0, 0.9), capturable=True)
-opt_d = th.optim.Adam(disc.parameters(), lr=1e-3, betas=(0.0, 0.9), capturable=True)
+opt_g = th.optim.Adam(gen.parameters(), lr=1e-3, betas=(0.0, 0.9), capturable=True, fused=True)
+opt_d = th.optim.Adam(disc.parameters(), lr=1e-3, betas=(0.0, 0.9), capturable=True, fused=True)
 gs = GraphedSteps(gen, disc, opt_g, opt_d, B, 32, 512, 0.5)
 x_real = th.rand(B, 2, 512, 512, device=dev) * 2 - 1
 for _ in range(3):
@@ -34,3 +34,6 @@ for name, fn in (("critic graph", lambda: gs.critic_step(x_real)), ("generator g
           f"gaps {(t1 - t0 - busy) / 1e3:.3f} ms")
     for k, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:24]:
         print(f"   {t / 1e3:8.3f} ms  {n:4d} x {t / n:7.1f} us  {k}")
+    for pat in ("k_conv3x3<", "k_conv3x3_wgrad", "k_lrelu_bwd", "k_wgrad_reduce"):
+        d = sorted(round(e.time_range.end - e.time_range.start, 1) for e in evs if pat in e.name)
+        print(f"   durations of {pat} (us): {d}")
