@@ -84,6 +84,36 @@ k_conv3x3_wgrad(const WgradParams p) {
     if (warp >= kProd0 && warp < kMma0) {
         // ================= producers: dy tile + x halo of the tile, 16-byte cp.async =================
         const int pt = tid - kProd0 * 32;
+        const int items_dy = 128 * nch_dy, items_x = kHaloPos * nch_x;
+        // Per-thread chunk tables, built once (tile independent because tiles start at even rows / columns): source
+        // offset from the tile origin in 16-byte units, and (y << 25) | (x << 21) | byte offset in the slot.  Tiles whose
+        // halo lies inside the image copy without any per-chunk border logic.  Layers wider than 64 channels take the
+        // generic loop for the chunks beyond the tables.
+        constexpr int kDyRegs = 8, kXRegs = 12;
+        int rel_dy[kDyRegs], rel_x[kXRegs];
+        uint32_t meta_dy[kDyRegs], meta_x[kXRegs];
+#pragma unroll
+        for (int k = 0; k < kDyRegs; ++k) {
+            const int i = pt + k * 128;
+            rel_dy[k] = 0; meta_dy[k] = 0xFFFFFFFFu;
+            if (i < items_dy) {
+                const int pix = (int)(((unsigned)i * p.idiv_dy.magic) >> 20), c = i - pix * nch_dy;
+                rel_dy[k] = ((pix >> 3) * p.W + (pix & 7)) * nch_dy + c;
+                meta_dy[k] = ((uint32_t)(pix >> 3) << 25) | ((uint32_t)(pix & 7) << 21) | ((uint32_t)(c * kDyPitch + pix) * 16u);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kXRegs; ++k) {
+            const int i = pt + k * 128;
+            rel_x[k] = 0; meta_x[k] = 0xFFFFFFFFu;
+            if (i < items_x) {
+                const int pos = (int)(((unsigned)i * p.idiv_x.magic) >> 20), c = i - pos * nch_x;
+                const int hy = (pos * 6554) >> 16, hx = pos - hy * kHaloW;
+                const int ry = p.upsample ? ((hy - 1) >> 1) : hy - 1, rx = p.upsample ? ((hx - 1) >> 1) : hx - 1;
+                rel_x[k] = (ry * p.Win + rx) * nch_x + c;
+                meta_x[k] = ((uint32_t)hy << 25) | ((uint32_t)hx << 21) | ((uint32_t)(c * kHaloPitch + pos) * 16u);
+            }
+        }
         int slot = 0; uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             mbar_wait(&empty[slot], ph ^ 1u);
@@ -93,20 +123,44 @@ k_conv3x3_wgrad(const WgradParams p) {
             const int oy0 = tyi * kTileH, ox0 = (tr - tyi * p.tiles_x) * kTileW;
             const uint32_t s_dy = smem_u32(stage0 + slot * stage_bytes);
             const uint32_t s_x = s_dy + (uint32_t)dy_bytes;
-            // dy tile: 128 pixels x nch_dy chunks (zero outside the image: those pixels must not contribute)
             const __nv_bfloat16* dyb = p.dy + (size_t)b * p.H * p.W * p.Cout;
-            const int items_dy = 128 * nch_dy;
-            for (int i = pt; i < items_dy; i += 128) {
+            const __nv_bfloat16* xb = p.x + (size_t)b * p.Hin * p.Win * p.Cin;
+            const uint4* org_dy = reinterpret_cast<const uint4*>(dyb + ((size_t)oy0 * p.W + ox0) * p.Cout);
+            const uint4* org_x = reinterpret_cast<const uint4*>(xb + ((size_t)(p.upsample ? oy0 >> 1 : oy0) * p.Win + (p.upsample ? ox0 >> 1 : ox0)) * p.Cin);
+            const bool interior = oy0 >= 1 && ox0 >= 1 && oy0 + kTileH + 1 <= p.H && ox0 + kTileW + 1 <= p.W;
+            if (interior) {
+#pragma unroll
+                for (int k = 0; k < kDyRegs; ++k)
+                    if (meta_dy[k] != 0xFFFFFFFFu) cp_async16_full(s_dy + (meta_dy[k] & 0x1FFFFFu), org_dy + rel_dy[k]);
+#pragma unroll
+                for (int k = 0; k < kXRegs; ++k)
+                    if (meta_x[k] != 0xFFFFFFFFu) cp_async16_full(s_x + (meta_x[k] & 0x1FFFFFu), org_x + rel_x[k]);
+            } else {
+                // dy tile: zero outside the image (those pixels must not contribute); x halo: zero padding
+#pragma unroll
+                for (int k = 0; k < kDyRegs; ++k) {
+                    if (meta_dy[k] != 0xFFFFFFFFu) {
+                        const bool ok = oy0 + (int)(meta_dy[k] >> 25) < p.H && ox0 + (int)((meta_dy[k] >> 21) & 0xF) < p.W;
+                        cp_async16(s_dy + (meta_dy[k] & 0x1FFFFFu), ok ? (const void*)(org_dy + rel_dy[k]) : (const void*)p.dy, ok ? 16u : 0u);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < kXRegs; ++k) {
+                    if (meta_x[k] != 0xFFFFFFFFu) {
+                        const int iy = oy0 - 1 + (int)(meta_x[k] >> 25), ix = ox0 - 1 + (int)((meta_x[k] >> 21) & 0xF);
+                        const bool ok = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+                        cp_async16(s_x + (meta_x[k] & 0x1FFFFFu), ok ? (const void*)(org_x + rel_x[k]) : (const void*)p.x, ok ? 16u : 0u);
+                    }
+                }
+            }
+            for (int i = pt + kDyRegs * 128; i < items_dy; i += 128) {
                 const int pix = (int)(((unsigned)i * p.idiv_dy.magic) >> 20), c = i - pix * nch_dy;
                 const int oy = oy0 + (pix >> 3), ox = ox0 + (pix & 7);
                 const bool ok = oy < p.H && ox < p.W;
                 const void* src = ok ? (const void*)(reinterpret_cast<const uint4*>(dyb + ((size_t)oy * p.W + ox) * p.Cout) + c) : (const void*)p.dy;
                 cp_async16(s_dy + (uint32_t)(c * kDyPitch + pix) * 16u, src, ok ? 16u : 0u);
             }
-            // x halo (same staging as the forward kernel)
-            const __nv_bfloat16* xb = p.x + (size_t)b * p.Hin * p.Win * p.Cin;
-            const int items_x = kHaloPos * nch_x;
-            for (int i = pt; i < items_x; i += 128) {
+            for (int i = pt + kXRegs * 128; i < items_x; i += 128) {
                 const int pos = (int)(((unsigned)i * p.idiv_x.magic) >> 20), c = i - pos * nch_x;
                 const int hy = (pos * 6554) >> 16, hx = pos - hy * kHaloW;
                 const int iy = oy0 - 1 + hy, ix = ox0 - 1 + hx;
