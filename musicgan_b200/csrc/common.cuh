@@ -1,5 +1,6 @@
 // Shared host/device helpers of the musicgan_b200 C-ABI library (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -29,6 +30,30 @@ struct ProfScope {
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- programmatic dependent launch ------------------------------------------------------------------------------
+// A training step is ~1000 short dependent kernels.  Launched with programmaticStreamSerialization the next kernel's
+// CTAs may become resident and run their on-chip prologue (barrier init, TMEM allocation, index tables) while the
+// previous kernel is still draining; `pdl_wait()` then blocks until that kernel has completed and its writes are
+// visible.  Rules kept by every kernel launched through launch_pdl(): pdl_trigger() first, pdl_wait() executed by EVERY
+// thread before its first global-memory access (reads AND writes: an output buffer may be recycled memory the previous
+// kernel still reads).  Without the launch attribute both instructions are no-ops.  MG_PDL=0 switches the attribute off.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    static const bool on = !(getenv("MG_PDL") && atoi(getenv("MG_PDL")) == 0);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = on ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
 
 // Monotone int key of a float (for atomicMin / atomicMax on floats of either sign).
 __device__ __forceinline__ int float_key(float x) {

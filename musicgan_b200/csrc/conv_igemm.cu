@@ -99,6 +99,10 @@ k_conv3x3(const ConvParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int acc_stride = p.acc_stride;
+    // Dependents may be scheduled only now that this CTA owns its TMEM columns: a dependent CTA that allocated first
+    // would sit in pdl_wait() holding columns this CTA needs in order to finish -- a deadlock.
+    pdl_trigger();
+    pdl_wait();                  // everything above overlapped the previous kernel's tail; global memory from here on
 
     if (warp >= kProdWarp0 && warp < kMmaWarp) {
         // ================= producers =================
@@ -348,6 +352,8 @@ __global__ void k_pack_weights(const float* __restrict__ w, int Cout, int Cin, i
     const int n_out = transpose_flip ? Cin : Cout, k_in = transpose_flip ? Cout : Cin;
     const int nch = k_in >> 3;
     const int total = 9 * n_out * k_in;
+    pdl_trigger();
+    pdl_wait();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         // destination order: slice, tap, chunk, n_local, e
         int r = i;
@@ -447,7 +453,7 @@ int mg_conv3x3_pack_weights(const float* w_f32, int Cin, int Cout, int dgrad, vo
     ProfScope ps("k_pack_weights", st);
     const int total = 9 * Cin * Cout;
     const int fwd_cout = dgrad ? Cin : Cout, fwd_cin = dgrad ? Cout : Cin;
-    k_pack_weights<<<(total + 255) / 256, 256, 0, st>>>(w_f32, fwd_cout, fwd_cin, dgrad ? 1 : 0, pl.Nt, (__nv_bfloat16*)packed);
+    launch_pdl(k_pack_weights, dim3((total + 255) / 256), dim3(256), 0, st, w_f32, fwd_cout, fwd_cin, dgrad ? 1 : 0, pl.Nt, (__nv_bfloat16*)packed);
     return check_launch("k_pack_weights");
 }
 
@@ -475,7 +481,7 @@ int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* 
         // w_f32 is [Cout_w][Cin_w][3][3] of the FORWARD convolution; for dgrad the GEMM's K (=Cin here) is the
         // forward Cout and the GEMM's N (=Cout here) the forward Cin
         const int fwd_cout = dgrad ? Cin : Cout, fwd_cin = dgrad ? Cout : Cin;
-        k_pack_weights<<<(total + 255) / 256, 256, 0, st>>>(w_f32, fwd_cout, fwd_cin, dgrad ? 1 : 0, pl.Nt, (__nv_bfloat16*)ws);
+        launch_pdl(k_pack_weights, dim3((total + 255) / 256), dim3(256), 0, st, w_f32, fwd_cout, fwd_cin, dgrad ? 1 : 0, pl.Nt, (__nv_bfloat16*)ws);
     }
     ConvParams p{};
     p.x = (const __nv_bfloat16*)x; p.wpack = (const uint4*)ws; p.bias = bias; p.y = (__nv_bfloat16*)y; p.inv_norm = inv_norm;
@@ -505,7 +511,7 @@ int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* 
     const int per_slice = max(1, min(p.n_tiles, ctas / pl.n_slices > 0 ? ctas / pl.n_slices : 1));
     {
         ProfScope ps(dgrad ? "k_conv3x3_dgrad" : "k_conv3x3_fprop", st);
-        kern<<<dim3(per_slice, pl.n_slices), (pl.epi_warps + 5) * 32, pl.smem, st>>>(p);
+        launch_pdl(kern, dim3(per_slice, pl.n_slices), dim3((pl.epi_warps + 5) * 32), pl.smem, st, p);
     }
     return check_launch("k_conv3x3");
 }

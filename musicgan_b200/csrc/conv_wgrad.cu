@@ -80,6 +80,8 @@ k_conv3x3_wgrad(const WgradParams p) {
     const uint32_t tmem_base = *tmem_slot;
     const int a_cols = p.blocks_per_cta * 64;                                  // columns of one A buffer
     const uint32_t tmem_a = tmem_base + (uint32_t)(p.tmem_cols - 2 * a_cols);  // two A buffers at the top
+    pdl_trigger();               // only after the TMEM allocation (see k_conv3x3: a dependent must not allocate first)
+    pdl_wait();                  // everything above overlapped the previous kernel's tail; global memory from here on
 
     if (warp >= kProd0 && warp < kMma0) {
         // ================= producers: dy tile + x halo of the tile, 16-byte cp.async =================
@@ -297,6 +299,8 @@ k_conv3x3_wgrad(const WgradParams p) {
 __global__ void __launch_bounds__(256)
 k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dw, int Cin, int Cout, int gx, int groups, int nb, FastDiv div_cin) {
     __shared__ float red[8][33];
+    pdl_trigger();
+    pdl_wait();
     const int total = 9 * Cin * Cout;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int t = blockIdx.x * 32 + lane;
@@ -397,12 +401,12 @@ extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, v
     cudaStream_t st = (cudaStream_t)stream;
     {
         ProfScope ps("k_conv3x3_wgrad", st);
-        k_conv3x3_wgrad<<<dim3(gx, groups, 1), kWgradThreads, smem, st>>>(p);
+        launch_pdl(k_conv3x3_wgrad, dim3(gx, groups, 1), dim3(kWgradThreads), smem, st, p);
     }
     {
         ProfScope ps("k_wgrad_reduce", st);
         const int total = 9 * Cin * Cout;
-        k_wgrad_reduce<<<(total + 31) / 32, 256, 0, st>>>((const float*)ws, dw, Cin, Cout, gx, groups, nb, p.div_cin);
+        launch_pdl(k_wgrad_reduce, dim3((total + 31) / 32), dim3(256), 0, st, (const float*)ws, dw, Cin, Cout, gx, groups, nb, p.div_cin);
     }
     return check_launch("k_conv3x3_wgrad");
 }

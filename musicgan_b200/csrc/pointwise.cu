@@ -42,6 +42,8 @@ __device__ __forceinline__ void block_colsum_to_row(const float (&acc)[8], float
 // gb[c] = sum_r part[r][c]; block = 8 warps x 32 consecutive channels, warp w takes rows w, w+8, ...
 __global__ void __launch_bounds__(256)
 k_colsum_reduce(const float* __restrict__ part, float* __restrict__ gb, int C, int rows) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[8][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
@@ -82,6 +84,8 @@ union Pack8 { uint4 u; __nv_bfloat162 h[4]; };
 __global__ void __launch_bounds__(256)
 k_rgb_expand(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
              const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y, int64_t HW, int C, int mode, int64_t total) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sw[];           // [C][2] then [C] bias
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sw[i] = w[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) sw[2 * C + i] = b ? b[i] : 0.0f;
@@ -119,6 +123,8 @@ __global__ void __launch_bounds__(256)
 k_rgb_project(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w2, int row_stride, int col_stride,
               const float* __restrict__ bias, const __nv_bfloat16* __restrict__ mask_src, float* __restrict__ out,
               int64_t HW, int C, int act, int64_t total) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sw[];           // [2][C]
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) { const int k = i / C, c = i - k * C; sw[i] = w2[k * row_stride + c * col_stride]; }
     __syncthreads();
@@ -153,6 +159,8 @@ k_rgb_project(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w2,
 __global__ void __launch_bounds__(256)
 k_rgb_wgrad(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ mask_src, const float* __restrict__ x,
             float* __restrict__ gw, float* __restrict__ gb, int64_t HW, int C, int64_t total) {
+    pdl_trigger();
+    pdl_wait();
     const int c0 = blockIdx.y * 8;
     float acc[8][3];
 #pragma unroll
@@ -195,6 +203,8 @@ k_rgb_wgrad(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict
 // ---- 2x2 average pooling, bf16 NHWC ---------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_pool2(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int Ho, int Wo, int C8, int64_t total, float scale) {
+    pdl_trigger();
+    pdl_wait();
     // one thread = 8 channels of one output pixel
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C8);
@@ -219,6 +229,8 @@ k_pool2(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, i
 // adjoint: out[b][2y+i][2x+j][c] = 0.25 * in[b][y][x][c]
 __global__ void __launch_bounds__(256)
 k_unpool2(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int Hi, int Wi, int C8, int64_t total) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C8);
         int64_t r = i / C8;
@@ -240,6 +252,8 @@ k_unpool2(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
 __global__ void __launch_bounds__(256)
 k_lrelu_bwd(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ gz,
             float* __restrict__ part, int C8, int64_t total, int64_t stride) {
+    pdl_trigger();
+    pdl_wait();
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
@@ -293,6 +307,8 @@ k_lrelu_bwd(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restric
 __global__ void __launch_bounds__(256)
 k_pixelnorm_lrelu_bwd(const __nv_bfloat16* __restrict__ go, const __nv_bfloat16* __restrict__ o, const float* __restrict__ inv,
                       __nv_bfloat16* __restrict__ gz, int C, int64_t n_pixels) {
+    pdl_trigger();
+    pdl_wait();
     const int C8 = C >> 3;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pixels; p += (int64_t)gridDim.x * blockDim.x) {
         const uint4* g4 = reinterpret_cast<const uint4*>(go + p * C);
@@ -327,6 +343,8 @@ k_pixelnorm_lrelu_bwd(const __nv_bfloat16* __restrict__ go, const __nv_bfloat16*
 // as k_lrelu_bwd
 __global__ void __launch_bounds__(256)
 k_colsum(const __nv_bfloat16* __restrict__ g, float* __restrict__ part, int C8, int64_t total, int64_t stride) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_t[256 * 9];
     float acc[8];
 #pragma unroll
@@ -358,7 +376,7 @@ int mg_rgb_expand_bf16(const float* x, const float* w, const float* b, const voi
     const int64_t total = (int64_t)B * HW;
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope ps("k_rgb_expand", st);
-    k_rgb_expand<<<grid_for(total), 256, 3 * C * sizeof(float), st>>>(x, w, b, (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)y, HW, C, mode, total);
+    launch_pdl(k_rgb_expand, dim3(grid_for(total)), dim3(256), 3 * C * sizeof(float), st, x, w, b, (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)y, HW, C, mode, total);
     return check_launch("k_rgb_expand");
 }
 
@@ -368,8 +386,8 @@ int mg_rgb_project_bf16(const void* a, const float* w2, int row_stride, int col_
     const int64_t total = (int64_t)B * HW;
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope ps("k_rgb_project", st);
-    k_rgb_project<<<grid_for(total), 256, 2 * C * sizeof(float), st>>>((const __nv_bfloat16*)a, w2, row_stride, col_stride, bias,
-                                                                      (const __nv_bfloat16*)mask_src, out, HW, C, act, total);
+    launch_pdl(k_rgb_project, dim3(grid_for(total)), dim3(256), 2 * C * sizeof(float), st, (const __nv_bfloat16*)a, w2, row_stride, col_stride, bias,
+               (const __nv_bfloat16*)mask_src, out, HW, C, act, total);
     return check_launch("k_rgb_project");
 }
 
@@ -379,7 +397,7 @@ int mg_rgb_wgrad_bf16(const void* g, const void* mask_src, const float* x, float
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope ps("k_rgb_wgrad", st);
     const unsigned gx = grid_for(total, 256 * 8, 148 * 2);      // every block ends with 24 same-address atomics: keep the tail short
-    k_rgb_wgrad<<<dim3(gx, C / 8), 256, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)mask_src, x, gw, gb, HW, C, total);
+    launch_pdl(k_rgb_wgrad, dim3(gx, C / 8), dim3(256), 0, st, (const __nv_bfloat16*)g, (const __nv_bfloat16*)mask_src, x, gw, gb, HW, C, total);
     return check_launch("k_rgb_wgrad");
 }
 
@@ -397,12 +415,12 @@ int mg_lrelu_bwd_bf16(const void* gy, const void* y, void* gz, float* gb, void* 
     const unsigned blocks = colsum_blocks(total, C8);
     {
         ProfScope ps("k_lrelu_bwd", st);
-        k_lrelu_bwd<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y, (__nv_bfloat16*)gz,
-                                            gb ? (float*)ws : nullptr, C8, total, (int64_t)blocks * 256);
+        launch_pdl(k_lrelu_bwd, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)gy, (const __nv_bfloat16*)y, (__nv_bfloat16*)gz,
+                   gb ? (float*)ws : (float*)nullptr, C8, total, (int64_t)blocks * 256);
     }
     if (gb) {
         ProfScope ps("k_colsum_reduce", st);
-        k_colsum_reduce<<<(C + 31) / 32, 256, 0, st>>>((const float*)ws, gb, C, (int)blocks);
+        launch_pdl(k_colsum_reduce, dim3((C + 31) / 32), dim3(256), 0, st, (const float*)ws, gb, C, (int)blocks);
     }
     return check_launch("k_lrelu_bwd");
 }
@@ -414,16 +432,16 @@ int mg_pixelnorm_lrelu_bwd_bf16(const void* go, const void* o, const float* inv_
     cudaStream_t st = (cudaStream_t)stream;
     {
         ProfScope ps("k_pixelnorm_lrelu_bwd", st);
-        k_pixelnorm_lrelu_bwd<<<grid_for(n_pixels, 256, 148 * 8), 256, 0, st>>>(
-            (const __nv_bfloat16*)go, (const __nv_bfloat16*)o, inv_norm, (__nv_bfloat16*)gz, C, n_pixels);
+        launch_pdl(k_pixelnorm_lrelu_bwd, dim3(grid_for(n_pixels, 256, 148 * 8)), dim3(256), 0, st,
+                   (const __nv_bfloat16*)go, (const __nv_bfloat16*)o, inv_norm, (__nv_bfloat16*)gz, C, n_pixels);
     }
     if (gb) {
         const int C8 = C / 8;
         const int64_t total = n_pixels * C8;
         const unsigned blocks = colsum_blocks(total, C8);
         ProfScope ps("k_colsum", st);
-        k_colsum<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)gz, (float*)ws, C8, total, (int64_t)blocks * 256);
-        k_colsum_reduce<<<(C + 31) / 32, 256, 0, st>>>((const float*)ws, gb, C, (int)blocks);
+        launch_pdl(k_colsum, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)gz, (float*)ws, C8, total, (int64_t)blocks * 256);
+        launch_pdl(k_colsum_reduce, dim3((C + 31) / 32), dim3(256), 0, st, (const float*)ws, gb, C, (int)blocks);
     }
     return check_launch("k_pixelnorm_lrelu_bwd");
 }
@@ -433,8 +451,8 @@ int mg_pool2_bf16(const void* in, void* out, int B, int Ho, int Wo, int C, int a
     const int64_t total = (int64_t)B * Ho * Wo * (C / 8);
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope ps(adjoint == 1 ? "k_unpool2" : "k_pool2", st);
-    if (adjoint != 1) k_pool2<<<grid_for(total), 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, Ho, Wo, C / 8, total, adjoint == 2 ? 1.0f : 0.25f);
-    else k_unpool2<<<grid_for(total), 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, Ho, Wo, C / 8, total);
+    if (adjoint != 1) launch_pdl(k_pool2, dim3(grid_for(total)), dim3(256), 0, st, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, Ho, Wo, C / 8, total, adjoint == 2 ? 1.0f : 0.25f);
+    else launch_pdl(k_unpool2, dim3(grid_for(total)), dim3(256), 0, st, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, Ho, Wo, C / 8, total);
     return check_launch("k_pool2");
 }
 
