@@ -39,6 +39,9 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // thread before its first global-memory access (reads AND writes: an output buffer may be recycled memory the previous
 // kernel still reads).  Without the launch attribute both instructions are no-ops.  MG_PDL=0 switches the attribute off.
 #if defined(__CUDACC__)
+// threadIdx.x read exactly once: under register pressure the compiler otherwise re-reads the special register (S2R, ~20
+// cycles) inside the per-tile loops of the warp-specialised kernels instead of keeping it live
+__device__ __forceinline__ int tid_x_once() { int t; asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t)); return t; }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

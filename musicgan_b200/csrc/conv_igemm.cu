@@ -68,7 +68,7 @@ template <bool kPN, bool kBA, bool kOcc4>
 __global__ void __launch_bounds__(kOcc4 ? 288 : kConvThreads, kOcc4 ? 4 : 2)
 k_conv3x3(const ConvParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid0 = threadIdx.x;
     const int nch = p.Cin >> 3;
     const int slice = blockIdx.y;
     const int n0 = slice * p.Nt;
@@ -87,18 +87,21 @@ k_conv3x3(const ConvParams p) {
     uint64_t* w_full = tmem_full + 2 * kMaxAcc;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
-    if (tid == 0) {
+    if (tid0 == 0) {
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full_a[i], 128); mbar_init(&empty_a[i], 1); }
         for (int i = 0; i < kMaxAcc; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
         mbar_init(w_full, 256);           // per producer thread: its cp.async group + one plain (release) arrive
         mbar_fence_init();
     }
-    if (warp == kMmaWarp) tmem_alloc(tmem_slot, p.tmem_cols);
+    if ((tid0 >> 5) == kMmaWarp) tmem_alloc(tmem_slot, p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int acc_stride = p.acc_stride;
+    // Thread index made opaque (bit 0 of a TMEM base address is always 0, but only at run time): ptxas otherwise
+    // re-reads %tid.x (S2R, tens of cycles) inside every per-tile loop instead of keeping it in a register.
+    const int tid = tid0 | (int)(tmem_base & 1u), warp = tid >> 5, lane = tid & 31;
     // Dependents may be scheduled only now that this CTA owns its TMEM columns: a dependent CTA that allocated first
     // would sit in pdl_wait() holding columns this CTA needs in order to finish -- a deadlock.
     pdl_trigger();

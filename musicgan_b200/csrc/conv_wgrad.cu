@@ -48,7 +48,7 @@ struct WgradParams {
 __global__ void __launch_bounds__(kWgradThreads, 1)
 k_conv3x3_wgrad(const WgradParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid0 = threadIdx.x;
     const int nch_x = p.Cin >> 3, nch_dy = p.Cout >> 3;
     const int blk0 = blockIdx.y * p.blocks_per_cta;
     const int nb = min(p.blocks_per_cta, p.n_blocks - blk0);
@@ -67,17 +67,20 @@ k_conv3x3_wgrad(const WgradParams p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 5);
 
     constexpr int kProd0 = kXposeWarps, kMma0 = kXposeWarps + 4;
-    if (tid == 0) {
+    if (tid0 == 0) {
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], kWgradMmaWarps + kXposeWarps); }
         for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], kXposeWarps); mbar_init(&a_empty[i], kWgradMmaWarps); }
         mbar_init(done, kWgradMmaWarps);
         mbar_fence_init();
     }
-    if (warp == kMma0) tmem_alloc(tmem_slot, p.tmem_cols);
+    if ((tid0 >> 5) == kMma0) tmem_alloc(tmem_slot, p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Thread index made opaque (bit 0 of a TMEM base address is always 0, but only at run time): ptxas otherwise
+    // re-reads %tid.x (S2R, tens of cycles) inside every per-tile loop instead of keeping it in a register.
+    const int tid = tid0 | (int)(tmem_base & 1u), warp = tid >> 5, lane = tid & 31;
     const int a_cols = p.blocks_per_cta * 64;                                  // columns of one A buffer
     const uint32_t tmem_a = tmem_base + (uint32_t)(p.tmem_cols - 2 * a_cols);  // two A buffers at the top
     pdl_trigger();               // only after the TMEM allocation (see k_conv3x3: a dependent must not allocate first)
