@@ -20,13 +20,17 @@ from .networks import ops
 
 class GraphedSteps:
     def __init__(self, gen, disc, optim_gen, optim_disc, batch: int, rand_channels: int, resolution: int, alpha: float,
-                 grad_sync_d=None, grad_sync_g=None, warmup: int = 3):
+                 grad_sync_d=None, grad_sync_g=None, warmup: int = 3, static_noise: bool = False):
         self.gen, self.disc, self.og, self.od = gen, disc, optim_gen, optim_disc
         self.batch, self.alpha = batch, alpha
         self.sync_d, self.sync_g = grad_sync_d, grad_sync_g
         dev = next(gen.parameters()).device
         self.x_real = th.zeros(batch, 2, resolution, resolution, device=dev)
         self.z_shape = (batch, rand_channels, 2, 2)
+        # static_noise: latent vectors and the penalty's uniform sample are graph INPUTS (self.z, self.eps) instead of
+        # being drawn inside the graph -- lets a test replay exactly what an eager step computes
+        self.z = th.zeros(self.z_shape, device=dev) if static_noise else None
+        self.eps = th.zeros(batch, 1, 1, 1, device=dev) if static_noise else None
         self.d_stats = self.g_stats = None
         self._gd = self._gg = None
         self._capture(warmup)
@@ -34,12 +38,12 @@ class GraphedSteps:
     # -- the two step bodies (static shapes, no host sync) -------------------------------------------------
     def _critic_body(self):
         gen, disc, alpha, n = self.gen, self.disc, self.alpha, self.batch
-        z = th.randn(self.z_shape, device=self.x_real.device)
+        z = self.z if self.z is not None else th.randn(self.z_shape, device=self.x_real.device)
         with th.no_grad():
             x_fake = gen(z, alpha)
         out = disc(th.cat([self.x_real, x_fake], dim=0), alpha)
         d_loss = networks.wasserstein_discriminator_loss(out[:n], out[n:])
-        gp = disc.gradient_penalty(self.x_real, x_fake, alpha)
+        gp = disc.gradient_penalty(self.x_real, x_fake, alpha, eps=self.eps)
         params = [p for p in disc.parameters()]
         grads = th.autograd.grad(d_loss + gp, params, allow_unused=True)
         for p, g in zip(params, grads):
@@ -51,7 +55,7 @@ class GraphedSteps:
 
     def _generator_body(self):
         gen, disc, alpha = self.gen, self.disc, self.alpha
-        z = th.randn(self.z_shape, device=self.x_real.device)
+        z = self.z if self.z is not None else th.randn(self.z_shape, device=self.x_real.device)
         # only G's gradients are needed (the reference computes and discards D's, train.py:208-214): with the critic
         # frozen its weight-gradient kernels are not even launched
         params = [p for p in gen.parameters()]

@@ -74,6 +74,16 @@ def invalidate_pack_cache() -> None:
     _pack_epoch[0] += 1
 
 
+# Fused optimisers (torch._fused_adam_, used by train.py) update parameters WITHOUT bumping Tensor._version, so the
+# version stamp alone would keep serving the packed copy of the previous weights.  Every optimiser step of the process
+# therefore starts a new cache epoch.
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook
+    register_optimizer_step_post_hook(lambda optimizer, args, kwargs: invalidate_pack_cache())
+except ImportError:      # pragma: no cover  (older torch: train_step invalidates explicitly)
+    pass
+
+
 def _packed_weights(w: th.Tensor, cin: int, cout: int, dgrad: bool):
     """Packed bf16 copy of a weight tensor, cached ON the parameter object per (version, storage address): parameters
     change once per optimiser step but are read by several forward / backward kernels.  The cache lives and dies with

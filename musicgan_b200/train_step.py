@@ -25,6 +25,7 @@ def critic_step(gen, disc, optim_disc, z, x_real, alpha: float, eps=None, step: 
     (disc_loss + grad_pen).backward()
     if step and optim_disc is not None:
         optim_disc.step()
+        networks.ops.invalidate_pack_cache()      # parameters changed (fused optimisers do not bump Tensor._version)
     return disc_loss.detach(), grad_pen.detach(), out_real.detach(), out_fake.detach()
 
 
@@ -56,4 +57,5 @@ def generator_step(gen, disc, optim_gen, z, alpha: float, step: bool = True):
         gen_loss.backward()
     if step and optim_gen is not None:
         optim_gen.step()
+        networks.ops.invalidate_pack_cache()
     return gen_loss.detach(), out_fake.detach()

@@ -225,3 +225,63 @@ def test_growth_and_shapes():
         grew = gen.next_layer()
         assert grew == disc.next_layer() == (s < 7)
     assert not gen.growing and not disc.growing
+
+
+def test_graph_replays_equal_eager_steps():
+    """bench.py's headline path replays CUDA graphs (graphed.py): the same latent vectors, penalty samples and real
+    batches must move the parameters exactly like the eager steps of train_step.py (same kernels, same order; only the
+    1x1-layer weight gradients use atomics, so agreement is to fp32 summation-order noise, amplified by Adam's
+    normalisation for near-zero gradients -> compared as update directions)."""
+    from musicgan_b200 import train_step
+    from musicgan_b200.graphed import GraphedSteps
+    stage, batch, alpha = 3, 4, 0.5
+    res = 4 * 2 ** stage
+    sd_g, sd_d = no.make_state("gen", stage, 21), no.make_state("disc", stage, 22)
+    pairs = []
+    for _ in range(2):
+        gen, disc = build(stage, sd_g, sd_d)
+        og = torch.optim.Adam(gen.parameters(), lr=1e-3, betas=(0.0, 0.9), capturable=True, fused=True)
+        od = torch.optim.Adam(disc.parameters(), lr=1e-3, betas=(0.0, 0.9), capturable=True, fused=True)
+        pairs.append((gen, disc, og, od))
+    (gen_e, disc_e, og_e, od_e), (gen_g, disc_g, og_g, od_g) = pairs
+    start = {k: v.detach().clone() for k, v in list(gen_e.named_parameters()) + list(disc_e.named_parameters())}
+    gs = GraphedSteps(gen_g, disc_g, og_g, od_g, batch, 32, res, alpha, warmup=1, static_noise=True)
+    # the warm-up before capture took optimiser steps: put parameters and Adam state back IN PLACE (the graphs hold
+    # the storages)
+    gen_g.load_state_dict({k: v.cuda() for k, v in sd_g.items()}, strict=True)
+    disc_g.load_state_dict({k: v.cuda() for k, v in sd_d.items()}, strict=True)
+    for opt in (og_g, od_g):
+        for st in opt.state.values():
+            st["exp_avg"].zero_(); st["exp_avg_sq"].zero_(); st["step"].zero_()
+    for k, p in list(gen_g.named_parameters()) + list(disc_g.named_parameters()):
+        assert torch.equal(p.detach(), start[k]), k
+    g = torch.Generator().manual_seed(5)
+    for it in range(3):
+        x_real = (torch.rand(batch, 2, res, res, generator=g) * 2 - 1).cuda()
+        z, z2 = torch.randn(batch, 32, 2, 2, generator=g).cuda(), torch.randn(batch, 32, 2, 2, generator=g).cuda()
+        eps = torch.rand(batch, 1, 1, 1, generator=g).cuda()
+        d_e = train_step.critic_step(gen_e, disc_e, od_e, z, x_real, alpha, eps=eps)
+        gs.z.copy_(z); gs.eps.copy_(eps)
+        stats = gs.critic_step(x_real).clone()
+        # d_loss = mean D(fake) - mean D(real) is a difference of nearly equal numbers: tolerance on their scale
+        scale = abs(d_e[2].mean().item()) + abs(d_e[3].mean().item())
+        print(f"it {it}: d_loss {stats[0].item():.3e} vs {d_e[0].item():.3e} (scale {scale:.3e}); gp {stats[1].item():.6f} vs {d_e[1].item():.6f}")
+        assert abs(stats[0].item() - d_e[0].item()) <= 1e-3 * scale
+        assert abs(stats[1].item() - d_e[1].item()) <= 1e-3 * abs(d_e[1].item())
+        g_e = train_step.generator_step(gen_e, disc_e, og_e, z2, alpha)
+        gs.z.copy_(z2)
+        gstats = gs.generator_step().clone()
+        print(f"it {it}: g_loss {gstats[0].item():.3e} vs {g_e[0].item():.3e}")
+        assert abs(gstats[0].item() - g_e[0].item()) <= 1e-3 * max(abs(g_e[0].item()), scale)
+    torch.cuda.synchronize()
+    named_g = dict(list(gen_g.named_parameters()) + list(disc_g.named_parameters()))
+    moved = 0
+    for k, pe in list(gen_e.named_parameters()) + list(disc_e.named_parameters()):
+        de, dg = (pe - start[k]).flatten().double(), (named_g[k] - start[k]).flatten().double()
+        if de.norm() == 0:
+            assert dg.norm() == 0, k              # blocks not in the active path stay untouched in both
+            continue
+        moved += 1
+        cos = (de @ dg / (de.norm() * dg.norm())).item()
+        assert cos >= 0.999, (k, cos)
+    assert moved > 10
