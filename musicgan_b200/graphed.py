@@ -11,6 +11,8 @@ alpha ramps and may switch to graphs once alpha == 1).
 """
 from __future__ import annotations
 
+import os
+
 import torch as th
 
 from . import networks
@@ -20,7 +22,8 @@ from .networks import ops
 
 class GraphedSteps:
     def __init__(self, gen, disc, optim_gen, optim_disc, batch: int, rand_channels: int, resolution: int, alpha: float,
-                 grad_sync_d=None, grad_sync_g=None, warmup: int = 3, static_noise: bool = False):
+                 grad_sync_d=None, grad_sync_g=None, warmup: int = 3, static_noise: bool = False,
+                 two_streams: bool = None):
         self.gen, self.disc, self.og, self.od = gen, disc, optim_gen, optim_disc
         self.batch, self.alpha = batch, alpha
         self.sync_d, self.sync_g = grad_sync_d, grad_sync_g
@@ -33,6 +36,17 @@ class GraphedSteps:
         self.eps = th.zeros(batch, 1, 1, 1, device=dev) if static_noise else None
         self.d_stats = self.g_stats = None
         self._gd = self._gg = None
+        # two_streams: the penalty branch (forward on x_hat, inner backward, double backward) and the Wasserstein branch
+        # (forward / backward on the real + fake batch) of the critic step only share read-only inputs, so they are
+        # captured as parallel branches of the graph: most of their ~600 launches are small-spatial layers that use a
+        # fraction of the SMs and now overlap pairwise
+        if two_streams is None:
+            two_streams = os.environ.get("MG_TWO_STREAMS", "1") != "0"
+        self._branch = th.cuda.Stream(device=dev) if two_streams else None
+        if two_streams and hasattr(th.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            # the parameters' AccumulateGrad nodes were created on another stream; gradients are collected by
+            # autograd.grad (never accumulated), so the mismatch the engine warns about is intended
+            th.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         self._capture(warmup)
 
     # -- the two step bodies (static shapes, no host sync) -------------------------------------------------
@@ -41,11 +55,24 @@ class GraphedSteps:
         z = self.z if self.z is not None else th.randn(self.z_shape, device=self.x_real.device)
         with th.no_grad():
             x_fake = gen(z, alpha)
-        out = disc(th.cat([self.x_real, x_fake], dim=0), alpha)
-        d_loss = networks.wasserstein_discriminator_loss(out[:n], out[n:])
-        gp = disc.gradient_penalty(self.x_real, x_fake, alpha, eps=self.eps)
         params = [p for p in disc.parameters()]
-        grads = th.autograd.grad(d_loss + gp, params, allow_unused=True)
+        if self._branch is None:
+            out = disc(th.cat([self.x_real, x_fake], dim=0), alpha)
+            d_loss = networks.wasserstein_discriminator_loss(out[:n], out[n:])
+            gp = disc.gradient_penalty(self.x_real, x_fake, alpha, eps=self.eps)
+            grads = th.autograd.grad(d_loss + gp, params, allow_unused=True)
+        else:
+            ops.prepack(disc)                      # from here on both branches only read the packed weights
+            main, branch = th.cuda.current_stream(), self._branch
+            branch.wait_stream(main)
+            with th.cuda.stream(branch):
+                gp = disc.gradient_penalty(self.x_real, x_fake, alpha, eps=self.eps)
+                grads_gp = th.autograd.grad(gp, params, allow_unused=True)
+            out = disc(th.cat([self.x_real, x_fake], dim=0), alpha)
+            d_loss = networks.wasserstein_discriminator_loss(out[:n], out[n:])
+            grads_w = th.autograd.grad(d_loss, params, allow_unused=True)
+            main.wait_stream(branch)
+            grads = [gw if gg is None else (gg if gw is None else gw + gg) for gw, gg in zip(grads_w, grads_gp)]
         for p, g in zip(params, grads):
             p.grad = g
         if self.sync_d is not None:

@@ -109,6 +109,17 @@ def _packed_weights(w: th.Tensor, cin: int, cout: int, dgrad: bool):
     return buf
 
 
+def prepack(module) -> None:
+    """Pack (or refresh) both orientations of every 3x3 weight of `module` on the current stream.  After this call the
+    forward / data-gradient kernels only READ the cached copies, so independent branches of a step may run on
+    different streams (graphed.py)."""
+    for p in module.parameters():
+        if p.dim() == 4 and tuple(p.shape[2:]) == (3, 3) and p.is_cuda and p.requires_grad and p.dtype == th.float32:
+            cout, cin = p.shape[0], p.shape[1]
+            _packed_weights(p, cin, cout, False)
+            _packed_weights(p, cout, cin, True)
+
+
 def _check_act(x: th.Tensor, name: str):
     if not (x.is_cuda and x.dtype == th.bfloat16 and x.dim() == 4):
         raise TypeError(f"{name}: expected a CUDA bf16 (B, C, H, W) tensor, got {x.dtype} {tuple(x.shape)} on {x.device}")
