@@ -311,9 +311,11 @@ k_conv3x3(const ConvParams p) {
                         pk[j] = *reinterpret_cast<const uint32_t*>(&h);
                     }
                     if (valid && !((p.ablate & 8) && pk[0] == 0x12345678u)) {
-                        uint4* d4 = reinterpret_cast<uint4*>(dst + u * 16);
-                        d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        // one 256-bit store = one full 32-byte sector per thread (two 16-byte stores reach L2 as two
+                        // partial-sector writes)
+                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                                     ::"l"(dst + u * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]),
+                                       "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
                     }
                 };
                 int u = u0;
