@@ -43,6 +43,7 @@ struct WgradParams {
     unsigned bar_offset;
     int tiles_per_img;
     FastDiv div_img, div_tx;
+    int ablate;                 // debug (MG_WGRAD_ABLATE): 1 no copies, 2 no MMAs, 4 no operand staging (ldmatrix / tcgen05.st)
 };
 
 __global__ void __launch_bounds__(kWgradThreads, 1)
@@ -133,7 +134,8 @@ k_conv3x3_wgrad(const WgradParams p) {
             const uint4* org_dy = reinterpret_cast<const uint4*>(dyb + ((size_t)oy0 * p.W + ox0) * p.Cout);
             const uint4* org_x = reinterpret_cast<const uint4*>(xb + ((size_t)(p.upsample ? oy0 >> 1 : oy0) * p.Win + (p.upsample ? ox0 >> 1 : ox0)) * p.Cin);
             const bool interior = oy0 >= 1 && ox0 >= 1 && oy0 + kTileH + 1 <= p.H && ox0 + kTileW + 1 <= p.W;
-            if (interior) {
+            if (p.ablate & 1) {
+            } else if (interior) {
 #pragma unroll
                 for (int k = 0; k < kDyRegs; ++k)
                     if (meta_dy[k] != 0xFFFFFFFFu) cp_async16_full(s_dy + (meta_dy[k] & 0x1FFFFFu), org_dy + rel_dy[k]);
@@ -190,7 +192,7 @@ k_conv3x3_wgrad(const WgradParams p) {
             tc_fence_after();
             if (lane == 0) {
                 const uint64_t db0 = b_desc0 + (uint64_t)(slot * stage_units);
-                for (int j = mw; j < nb; j += kWgradMmaWarps) {
+                for (int j = mw; j < ((p.ablate & 2) ? 0 : nb); j += kWgradMmaWarps) {
                     const uint32_t d = tmem_base + j * p.Cout;
                     const uint32_t a0 = tmem_a + buf * a_cols + j * 64;
                     uint64_t db = db0;
@@ -249,7 +251,7 @@ k_conv3x3_wgrad(const WgradParams p) {
             for (int j = 0; j < kMaxBlocks; ++j) {
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
-                    if (goff[j][g] >= 0) {
+                    if (goff[j][g] >= 0 && !(p.ablate & 4)) {
                         const uint32_t ta = tmem_a + buf * a_cols + j * 64 + khalf * 32 + lane_addr + ((uint32_t)(g * 16) << 16);
                         const uint32_t src = s_x + (uint32_t)goff[j][g];
 #pragma unroll
@@ -391,6 +393,7 @@ extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, v
     }
     if (stages < 1) return MG_ERR_UNSUPPORTED;
     p.stages = stages;
+    p.ablate = getenv("MG_WGRAD_ABLATE") ? atoi(getenv("MG_WGRAD_ABLATE")) : 0;
     p.idiv_x = make_item_div(Cin / 8);
     p.idiv_dy = make_item_div(Cout / 8);
     p.div_cin = make_fast_div(Cin);

@@ -13,12 +13,15 @@ if op == "fprop":
     w = th.randn(co, ci, 3, 3, device="cuda").requires_grad_(True)
     bias = th.randn(co, device="cuda")
     fn = lambda: ops.conv3x3(x, w, bias, lrelu=True)
-else:       # x plays dY (ci channels); the forward weight is (ci, co, 3, 3); the result has co channels
+elif op == "dgrad":       # x plays dY (ci channels); the forward weight is (ci, co, 3, 3); the result has co channels
     w = th.randn(ci, co, 3, 3, device="cuda").requires_grad_(True)
     fn = lambda: ops.conv3x3(x, w, None, dgrad=True)
+else:                     # wgrad: MG_WGRAD_ABLATE masks (1 no copies, 2 no MMAs, 4 no operand staging)
+    dy = th.randn(B, co, H, H, device="cuda").bfloat16().contiguous(memory_format=th.channels_last)
+    fn = lambda: ops.conv3x3_wgrad(dy, x)
 out = []
 for mask in [int(m) for m in os.environ.get("MASKS", "0,1,2,4,8,16,3,5,6,7").split(",")]:
-    os.environ["MG_CONV_ABLATE"] = str(mask)
+    os.environ["MG_WGRAD_ABLATE" if op == "wgrad" else "MG_CONV_ABLATE"] = str(mask)
     for _ in range(3):
         fn()
     th.cuda.synchronize()
@@ -28,6 +31,6 @@ for mask in [int(m) for m in os.environ.get("MASKS", "0,1,2,4,8,16,3,5,6,7").spl
     th.cuda.synchronize()
     prof = _lib.profile_collect(64)
     _lib.profile_enable(False)
-    t = sum(v[0] for k, v in prof.items() if k.startswith("k_conv3x3")) / 20 * 1e3
+    t = sum(v[0] for k, v in prof.items() if k.startswith("k_conv3x3")) / 20 * 1e3      # (wgrad: without the reduce kernel)
     out.append(f"{mask}:{t:.1f}")
 print(op, ci, co, H, B, " ".join(out))
