@@ -306,6 +306,15 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first
+    # communicator): everything goes to stderr while the bench runs, the result line goes to the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
@@ -320,7 +329,7 @@ def main():
             elif sec is not None:
                 res["secondary"] = sec
         if res is not None:
-            print(json.dumps(res))
+            emit(res)
         return
 
     rank, world, local = dist_setup(args.gpus)
@@ -338,7 +347,7 @@ def main():
         elif res is not None and sec is not None:
             res["secondary"] = sec
     if rank == 0 and res is not None:
-        print(json.dumps(res))
+        emit(res)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
