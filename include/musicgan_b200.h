@@ -168,6 +168,12 @@ size_t mg_colsum_workspace_bytes(int C);
  * (backward of the Conv2d + LeakyReLU pairs, discriminator.py:15-22,26-33) */
 int mg_lrelu_bwd_bf16(const void* gy, const void* y, void* gz, float* gb, void* ws, size_t ws_bytes,
                       int64_t n_pixels, int C, mgStream stream);
+/* Backward of LeakyReLU -> AvgPool2d(2,2) in one pass (discriminator.py:15-24, ConvBlock): gp [B][Hi][Wi][C] is the
+ * gradient of the pooled tensor, h [B][2Hi][2Wi][C] the LeakyReLU output that was pooled;
+ * gz = 0.25 * upsample(gp) * mask(h) (bf16 NHWC, full resolution), gb[c] = sum over pixels of gz (OVERWRITTEN, may be
+ * NULL; needs ws of mg_colsum_workspace_bytes(C)).  Same values as mg_pool2_bf16(adjoint) followed by mg_lrelu_bwd_bf16. */
+int mg_unpool2_lrelu_bwd_bf16(const void* gp, const void* h, void* gz, float* gb, void* ws, size_t ws_bytes,
+                              int B, int Hi, int Wi, int C, mgStream stream);
 /* PixelNorm + LeakyReLU backward of a generator half-block (layers.py:11-17 after generator.py:23,38):
  * go, o [n_pixels][C] bf16 (o = the normalised forward output), inv_norm [n_pixels] fp32 (from mg_conv3x3_bf16 flag 2)
  * -> gz [n_pixels][C] bf16 = gradient w.r.t. the convolution output (+bias), gb[c] = sum over pixels (OVERWRITTEN, may be

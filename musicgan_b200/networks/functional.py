@@ -147,6 +147,49 @@ class LReLUBwd(Function):
         return (_act(g) * _lrelu_mask(y)), None, None
 
 
+class UnpoolLReLUBwd(Function):
+    """(gz, gb) = (0.25 * up2(gp) * mask(h), sum_pixels gz): the backward of LeakyReLU -> AvgPool2d(2, 2) in one kernel.
+    Linear in gp; its own backward is the masked multiply followed by the pooling (existing kernels)."""
+
+    @staticmethod
+    def forward(ctx, gp, h, want_bias_grad=True):
+        ctx.save_for_backward(h)
+        ctx.set_materialize_grads(False)
+        return ops.unpool_lrelu_bwd(gp, h, want_bias_grad=bool(want_bias_grad))
+
+    @staticmethod
+    def backward(ctx, ggz, ggb):
+        (h,) = ctx.saved_tensors
+        if ggz is None and ggb is None:
+            return None, None, None
+        if ggb is None:
+            return Pool2.apply(LReLUBwd.apply(ggz, h, False)[0]), None, None
+        g = ggb.float()[None, :, None, None].expand(h.shape)
+        if ggz is not None:
+            g = g + ggz.float()
+        return Pool2.apply(_act(g) * _lrelu_mask(h)), None, None
+
+
+class ConvBiasLReLUPool(Function):
+    """p = AvgPool2d(2,2)(LeakyReLU_0.2(conv3x3(x, w) + b)): first half of the discriminator's ConvBlock
+    (discriminator.py:15-24).  Forward = the fused conv kernel + the pooling kernel; backward starts with ONE kernel for
+    un-pooling, LeakyReLU mask and bias gradient (UnpoolLReLUBwd), then ConvDgrad / ConvWgrad."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        h = ops.conv3x3(_act(x), w.float().contiguous(), b.float().contiguous(), lrelu=True)
+        ctx.save_for_backward(x, w, h)
+        return ops.pool2(h)
+
+    @staticmethod
+    def backward(ctx, gp):
+        x, w, h = ctx.saved_tensors
+        gz, gb = UnpoolLReLUBwd.apply(gp, h, ctx.needs_input_grad[2] and _param_grads[0])
+        gx = ConvDgrad.apply(gz, w) if ctx.needs_input_grad[0] else None
+        gw = ConvWgrad.apply(gz, x) if ctx.needs_input_grad[1] and _param_grads[0] else None
+        return gx, gw, (gb if ctx.needs_input_grad[2] else None)
+
+
 class GenConv(Function):
     """One generator half-block: [nearest x2 upsample ->] conv3x3 + bias -> LeakyReLU(0.2) -> PixelNorm, all in one
     kernel (generator.py:16-24 / :26-40, layers.py:11-17).  First-order backward only (the generator is never

@@ -52,6 +52,7 @@ def _l():
         l.mg_colsum_workspace_bytes.argtypes = [c_int]
         l.mg_pixelnorm_lrelu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int64, c_int, c_void_p]
         l.mg_lrelu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int64, c_int, c_void_p]
+        l.mg_unpool2_lrelu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]
         l.mg_conv3x3_pack_weights.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]
         _declared = True
     return l
@@ -294,4 +295,22 @@ def lrelu_bwd(gy: th.Tensor, y: th.Tensor, want_bias_grad: bool = True):
         _lib.check(l.mg_lrelu_bwd_bf16(gy.data_ptr(), y.data_ptr(), gz.data_ptr(), gb.data_ptr() if gb is not None else None,
                                        ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
                                        B * H * W, C, _stream()), "mg_lrelu_bwd_bf16")
+    return gz, gb
+
+
+def unpool_lrelu_bwd(gp: th.Tensor, h: th.Tensor, want_bias_grad: bool = True):
+    """Backward of LeakyReLU -> AvgPool2d(2,2) in one pass: gz = 0.25 * up2(gp) * (h > 0 ? 1 : 0.2) at the resolution of
+    `h`, and the bias gradient sum over pixels (fp32)."""
+    gp = as_act(gp)
+    _check_act(h, "unpool_lrelu_bwd h")
+    B, C, H, W = h.shape
+    assert gp.shape == (B, C, H // 2, W // 2) and H % 2 == 0 and W % 2 == 0, (gp.shape, h.shape)
+    gz = th.empty_like(h)
+    gb = th.empty((C,), dtype=th.float32, device=h.device) if want_bias_grad else None
+    l = _l()
+    ws = _workspace(h.device, l.mg_colsum_workspace_bytes(C), "colsum") if want_bias_grad else None
+    with th.cuda.device(h.device):
+        _lib.check(l.mg_unpool2_lrelu_bwd_bf16(gp.data_ptr(), h.data_ptr(), gz.data_ptr(), gb.data_ptr() if gb is not None else None,
+                                               ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
+                                               B, H // 2, W // 2, C, _stream()), "mg_unpool2_lrelu_bwd_bf16")
     return gz, gb

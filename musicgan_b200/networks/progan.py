@@ -145,8 +145,7 @@ class ConvBlock(nn.Sequential):
                          _conv3(out_channels, out_channels), nn.LeakyReLU(2e-1))
 
     def forward(self, x: th.Tensor) -> th.Tensor:
-        h = fn.ConvBiasLReLU.apply(x, self[0].weight, self[0].bias)
-        h = fn.Pool2.apply(h)
+        h = fn.ConvBiasLReLUPool.apply(x, self[0].weight, self[0].bias)      # conv + LReLU, pool; fused backward
         return fn.ConvBiasLReLU.apply(h, self[3].weight, self[3].bias)
 
 

@@ -195,3 +195,20 @@ def test_pixelnorm_lrelu_backward_kernel():
     assert rel_l2(gz, auto) <= 2e-2          # vs exact autograd: only the bf16 rounding of the saved output differs
     s = ops.pool2(go, sum_pool=True)
     assert rel_l2(s, F.avg_pool2d(go.float(), 2) * 4) <= 4e-3
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 16, 16), (3, 48, 40, 24), (1, 160, 4, 4), (8, 16, 64, 32)])
+def test_unpool_lrelu_backward_kernel(B, C, H, W):
+    """mg_unpool2_lrelu_bwd_bf16 == mg_pool2_bf16(adjoint) followed by mg_lrelu_bwd_bf16: identical bf16 values
+    (0.25 * g is exact), bias sums equal up to fp32 summation order; both bias-gradient variants."""
+    from musicgan_b200.networks import ops
+    gp = _mk(B, C, H // 2, W // 2, 31)
+    h = _mk(B, C, H, W, 32)
+    gz_ref, gb_ref = ops.lrelu_bwd(ops.pool2(gp, adjoint=True), h)
+    gz, gb = ops.unpool_lrelu_bwd(gp, h)
+    assert torch.equal(gz, gz_ref)
+    assert torch.allclose(gb, gb_ref, rtol=1e-5, atol=1e-4 * gb_ref.abs().max().item())
+    exact = (0.25 * F.interpolate(gp.float(), scale_factor=2.0, mode="nearest") * torch.where(h.float() > 0, 1.0, 0.2)).sum(dim=(0, 2, 3))
+    assert torch.allclose(gb, exact, rtol=1e-4, atol=1e-4 * exact.abs().max().item())
+    gz2, none = ops.unpool_lrelu_bwd(gp, h, want_bias_grad=False)
+    assert none is None and torch.equal(gz2, gz_ref)
