@@ -126,13 +126,16 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
     conv_launch_list, ops.FLOPS["launches"] = ops.FLOPS["launches"], None
     value = world * args.steps / (ms * 1e-3)
 
-    # end to end: real batch from pinned host memory every step, loss read back
-    dev_in = th.empty_like(reals_dev[0])
+    # end to end through the public API: every step's real batch comes from pinned host memory (utils.DevicePrefetcher,
+    # the loader wrapper `train` uses: the upload of batch t+1 is issued on a copy stream while step t computes) and the
+    # loss is read back
+    import itertools
+    from .utils import DevicePrefetcher
     host_loss = th.empty((), dtype=th.float32).pin_memory()
+    feed = DevicePrefetcher((reals_host[i % n_real] for i in itertools.count()), dev, depth=2)
 
     def e2e_step():
-        dev_in.copy_(reals_host[it[0] % n_real], non_blocking=True)
-        loss = one_iter(dev_in)
+        loss = one_iter(next(feed))
         host_loss.copy_(loss, non_blocking=True)
 
     e2e_steps = max(5, min(args.steps, 10))

@@ -16,7 +16,7 @@ from torch.utils.data import DataLoader
 from tqdm import tqdm
 
 from . import audio, networks, parallel, train_step
-from .utils import Grower, Saver
+from .utils import DevicePrefetcher, Grower, Saver
 
 try:                                    # observability only, never on the hot path
     import mlflow
@@ -84,11 +84,11 @@ def train(run_name: str, input_dataset_path: str, output_dir: str, *,
     for e in range(nb_epoch):
         if sampler is not None:
             sampler.set_epoch(e)
-        bar = tqdm(loader, disable=rank != 0)
+        bar = tqdm(DevicePrefetcher(loader, th.device("cuda", th.cuda.current_device())), total=len(loader), disable=rank != 0)
         for x_real in bar:
             # the reference normalises / resizes on the CPU and then uploads (train.py:139-140); here the fp64 chunk is
-            # uploaded once and everything else happens on the GPU
-            x_real = grower.scale_transform(x_real.cuda(non_blocking=True).to(th.float))
+            # uploaded once (one step ahead, on a copy stream) and everything else happens on the GPU
+            x_real = grower.scale_transform(x_real.to(th.float))
             alpha = grower.alpha
 
             z = th.randn(batch_size, rand_channels, height, width, device="cuda")

@@ -31,6 +31,47 @@ def antialias_bilinear_matrix(in_size: int, out_size: int, device=None) -> th.Te
     return m.to(dtype=th.float32, device=device)
 
 
+class DevicePrefetcher:
+    """Iterate over (pinned) host batches and yield device tensors whose host->device copy was issued `depth` steps
+    ahead on a separate stream, so the upload of batch t+1 overlaps the compute of batch t (the reference uploads
+    synchronously inside the step, train.py:139-140)."""
+
+    def __init__(self, iterable, device, depth: int = 2):
+        import collections
+        self.it, self.dev = iter(iterable), th.device(device)
+        self.stream = th.cuda.Stream(self.dev)
+        self.queue = collections.deque()
+        for _ in range(max(1, depth)):
+            self._issue()
+
+    def _issue(self):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            return
+        with th.cuda.stream(self.stream):
+            dev_t = host.to(self.dev, non_blocking=True)
+            ev = th.cuda.Event()
+            ev.record(self.stream)
+        self.queue.append((dev_t, ev, host))          # `host` kept alive until its copy has been consumed
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if not self.queue:
+            raise StopIteration
+        dev_t, ev, _ = self.queue.popleft()
+        cur = th.cuda.current_stream(self.dev)
+        cur.wait_event(ev)
+        dev_t.record_stream(cur)
+        self._issue()
+        return dev_t
+
+    def __len__(self):
+        return len(self.it) if hasattr(self.it, "__len__") else NotImplemented
+
+
 class Grower:
     """Sample-count driven growth schedule (utils.py:14-86)."""
 

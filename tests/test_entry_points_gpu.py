@@ -71,3 +71,19 @@ def test_train_runs_grows_and_checkpoints(tmp_path):
     assert "gen_0.pt" in saved and "disc_1.pt" in saved and "optim_gen_0.pt" in saved
     sd = torch.load(str(out / "gen_0.pt"))
     assert "_Generator__gen_blocks.0.0.weight" in sd and all(torch.isfinite(v).all() for v in sd.values())
+
+
+def test_device_prefetcher_order_and_content():
+    """utils.DevicePrefetcher (the loader wrapper of `train` and of bench.py's end-to-end loop): batches arrive on the
+    device in order and intact although their uploads run one or two steps ahead on a copy stream."""
+    import torch
+    from musicgan_b200.utils import DevicePrefetcher
+    g = torch.Generator().manual_seed(0)
+    host = [torch.randn(4, 2, 64, 64, generator=g).pin_memory() for _ in range(7)]
+    got = []
+    for x in DevicePrefetcher(iter(host), "cuda:0", depth=2):
+        assert x.is_cuda
+        got.append((x * 2.0).cpu())          # consume on the current stream
+    assert len(got) == len(host)
+    for a, b in zip(got, host):
+        assert torch.equal(a, b * 2.0)
