@@ -114,6 +114,10 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
     _lib.profile_enable(True)
     ops.FLOPS.update(count=0.0, bytes=0.0, launches=[])
     for _ in range(prof_iters):
+        # an eager iteration is host bound (~1000 launches): without a head start for the host every event pair would
+        # also time the gap in which the GPU waits for the next launch to be submitted.  A spin kernel keeps the GPU
+        # busy while the host queues the whole iteration behind it.
+        th.cuda._sleep(int(0.06 * 1.9e9))
         step()
     th.cuda.synchronize()
     prof = _lib.profile_collect(64)
@@ -182,7 +186,8 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
                              "bytes": "x read once + y written once per launch (wgrad: dy + x read), weights excluded"},
                      "per_launch_bound_frac": t_bound / conv_s if conv_ms > 0 else 0.0,
                      "kernel_timing": "event pairs around every library kernel in an eager pass of the same 5-iteration schedule "
-                                      "right after the timed region (graph replays cannot carry event pairs)" if use_graphs else "timed region",
+                                      "right after the timed region, queued behind a spin kernel so the pairs do not time host "
+                                      "launch gaps (graph replays cannot carry event pairs)" if use_graphs else "timed region",
                      "conv_ms_per_step": conv_ms / args.steps, "conv_launches_per_step": conv_launches / args.steps,
                      "step_algorithmic_tflops": step_tf, "step_frac": step_tf / pk["tf_sus"],
                      "kernel_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}},
