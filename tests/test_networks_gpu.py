@@ -285,3 +285,33 @@ def test_graph_replays_equal_eager_steps():
         cos = (de @ dg / (de.norm() * dg.norm())).item()
         assert cos >= 0.999, (k, cos)
     assert moved > 10
+
+
+def test_repeated_steps_are_bitwise_reproducible():
+    """Race / hazard detector in place of compute-sanitizer (closed on this pool): with programmatic dependent launch,
+    early accumulator release, deterministic two-step reductions and the two-stream critic graph, the SAME critic step
+    on the SAME inputs must give bit-identical convolution weight / bias gradients, losses and penalties every time
+    (only the 1x1-layer gradients use atomics and may differ in the last bits)."""
+    from musicgan_b200 import train_step
+    stage, batch, alpha = 4, 4, 0.5
+    res = 4 * 2 ** stage
+    gen, disc = build(stage, no.make_state("gen", stage, 31), no.make_state("disc", stage, 32))
+    g = torch.Generator().manual_seed(9)
+    x_real = (torch.rand(batch, 2, res, res, generator=g) * 2 - 1).cuda()
+    z = torch.randn(batch, 32, 2, 2, generator=g).cuda()
+    eps = torch.rand(batch, 1, 1, 1, generator=g).cuda()
+    ref = None
+    for rep in range(12):
+        d_loss, gp, out_real, out_fake = train_step.critic_step(gen, disc, None, z, x_real, alpha, eps=eps, step=False)
+        snap = {"d_loss": d_loss.clone(), "gp": gp.clone(), "out_real": out_real.clone(), "out_fake": out_fake.clone()}
+        for k, p in disc.named_parameters():
+            if p.grad is not None and p.dim() == 4 and tuple(p.shape[2:]) == (3, 3):
+                snap[k] = p.grad.clone()
+            elif p.grad is not None and p.dim() == 1 and "conv_blocks" in k:
+                snap[k] = p.grad.clone()
+        if ref is None:
+            ref = snap
+            assert len(ref) > 20
+            continue
+        for k, v in snap.items():
+            assert torch.equal(v, ref[k]), (rep, k, (v.float() - ref[k].float()).abs().max().item())
