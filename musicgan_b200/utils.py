@@ -34,14 +34,21 @@ def antialias_bilinear_matrix(in_size: int, out_size: int, device=None) -> th.Te
 class DevicePrefetcher:
     """Iterate over (pinned) host batches and yield device tensors whose host->device copy was issued `depth` steps
     ahead on a separate stream, so the upload of batch t+1 overlaps the compute of batch t (the reference uploads
-    synchronously inside the step, train.py:139-140)."""
+    synchronously inside the step, train.py:139-140).
+
+    The device buffers are a fixed ring (no allocation per batch: an allocator round trip in the middle of a step costs
+    far more than the copy).  A yielded tensor stays valid until the NEXT batch is requested; work enqueued on the
+    current stream before that request is ordered before the buffer's reuse."""
 
     def __init__(self, iterable, device, depth: int = 2):
         import collections
         self.it, self.dev = iter(iterable), th.device(device)
         self.stream = th.cuda.Stream(self.dev)
         self.queue = collections.deque()
-        for _ in range(max(1, depth)):
+        self.depth = max(1, depth)
+        self.bufs, self.free_ev = [], []
+        self.issued, self.last = 0, None
+        for _ in range(self.depth):
             self._issue()
 
     def _issue(self):
@@ -49,11 +56,21 @@ class DevicePrefetcher:
             host = next(self.it)
         except StopIteration:
             return
+        k = self.issued % (self.depth + 2)
+        if len(self.bufs) <= k:
+            self.bufs.append(None)
+            self.free_ev.append(None)
+        buf = self.bufs[k]
+        if buf is None or buf.shape != host.shape or buf.dtype != host.dtype:
+            buf = self.bufs[k] = th.empty(host.shape, dtype=host.dtype, device=self.dev)
         with th.cuda.stream(self.stream):
-            dev_t = host.to(self.dev, non_blocking=True)
+            if self.free_ev[k] is not None:
+                self.stream.wait_event(self.free_ev[k])      # the consumer is done with the previous content
+            buf.copy_(host, non_blocking=True)
             ev = th.cuda.Event()
             ev.record(self.stream)
-        self.queue.append((dev_t, ev, host))          # `host` kept alive until its copy has been consumed
+        self.queue.append((k, ev, host))              # `host` kept alive until its copy has been consumed
+        self.issued += 1
 
     def __iter__(self):
         return self
@@ -61,12 +78,16 @@ class DevicePrefetcher:
     def __next__(self):
         if not self.queue:
             raise StopIteration
-        dev_t, ev, _ = self.queue.popleft()
         cur = th.cuda.current_stream(self.dev)
+        if self.last is not None:                     # everything enqueued so far used the previous batch at most
+            ev = th.cuda.Event()
+            ev.record(cur)
+            self.free_ev[self.last] = ev
+        k, ev, _ = self.queue.popleft()
         cur.wait_event(ev)
-        dev_t.record_stream(cur)
+        self.last = k
         self._issue()
-        return dev_t
+        return self.bufs[k]
 
     def __len__(self):
         return len(self.it) if hasattr(self.it, "__len__") else NotImplemented
