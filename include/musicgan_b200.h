@@ -160,6 +160,10 @@ int mg_rgb_project_bf16(const void* a, const float* w2, int row_stride, int col_
                         float* out, int B, int64_t HW, int C, int act, mgStream stream);
 int mg_rgb_wgrad_bf16(const void* g, const void* mask_src, const float* x, float* gw, float* gb, int B, int64_t HW, int C, mgStream stream);
 int mg_pool2_bf16(const void* in, void* out, int B, int Ho, int Wo, int C, int adjoint, mgStream stream);
+/* AvgPool2d(2,2) on fp32 NCHW planes (network input on the fade-in path, discriminator.py:130-133):
+ * adjoint 0: in [n_planes][2Ho][2Wo] -> out [n_planes][Ho][Wo]; adjoint 1: its backward, in [n_planes][Ho][Wo] ->
+ * out [n_planes][2Ho][2Wo] = 0.25 * in replicated.  Bit-identical to torch.nn.functional.avg_pool2d / its backward. */
+int mg_pool2_planes_f32(const float* in, float* out, int64_t n_planes, int Ho, int Wo, int adjoint, mgStream stream);
 /* Scratch of the per-channel sums below: one row of C partial sums per thread block, summed by a second small kernel in
  * a fixed order (deterministic, no atomics). */
 size_t mg_colsum_workspace_bytes(int C);

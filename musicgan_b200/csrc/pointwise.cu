@@ -246,6 +246,29 @@ k_unpool2(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
     }
 }
 
+// ---- AvgPool2d(2,2) on fp32 NCHW planes (the network input on the fade-in path, discriminator.py:130-133) ----------
+// adjoint 0: in [n][2Ho][2Wo] -> out [n][Ho][Wo] = ((a + b) + c) + d) * 0.25 (torch's summation order: bit-identical);
+// adjoint 1: in [n][Ho][Wo] -> out [n][2Ho][2Wo] = 0.25 * in replicated (its backward).  One thread per low-res element.
+__global__ void __launch_bounds__(256)
+k_pool2_planes(const float* __restrict__ in, float* __restrict__ out, int Ho, int Wo, int64_t total, int adjoint) {
+    pdl_trigger();
+    pdl_wait();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % Wo);
+        const int64_t r = i / Wo;                       // plane * Ho + y
+        const int64_t hi = (r * 2) * (int64_t)(2 * Wo) + 2 * x;        // top-left element of the 2x2 block
+        if (!adjoint) {
+            const float2 t = *reinterpret_cast<const float2*>(in + hi);
+            const float2 b = *reinterpret_cast<const float2*>(in + hi + 2 * Wo);
+            out[i] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(t.x, t.y), b.x), b.y), 0.25f);
+        } else {
+            const float v = 0.25f * in[i];
+            *reinterpret_cast<float2*>(out + hi) = make_float2(v, v);
+            *reinterpret_cast<float2*>(out + hi + 2 * Wo) = make_float2(v, v);
+        }
+    }
+}
+
 // ---- LeakyReLU backward + bias gradient ------------------------------------------------------------
 // gz = gy * mask(y) (bf16 NHWC), gb[c] += sum_pixels gz[.,c].  grid.x blocks x 256 threads; a thread keeps the same
 // 8-channel chunk for all its pixels (grid stride is a multiple of C/8), so its 8 partial sums stay in registers.
@@ -449,6 +472,15 @@ int mg_rgb_wgrad_bf16(const void* g, const void* mask_src, const float* x, float
     const unsigned gx = grid_for(total, 256 * 8, 148 * 2);      // every block ends with 24 same-address atomics: keep the tail short
     launch_pdl(k_rgb_wgrad, dim3(gx, C / 8), dim3(256), 0, st, (const __nv_bfloat16*)g, (const __nv_bfloat16*)mask_src, x, gw, gb, HW, C, total);
     return check_launch("k_rgb_wgrad");
+}
+
+int mg_pool2_planes_f32(const float* in, float* out, int64_t n_planes, int Ho, int Wo, int adjoint, mgStream stream) {
+    if (!in || !out || n_planes <= 0 || Ho <= 0 || Wo <= 0) return MG_ERR_BAD_ARG;
+    const int64_t total = n_planes * Ho * Wo;
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope ps("k_pool2_planes", st);
+    launch_pdl(k_pool2_planes, dim3(grid_for(total)), dim3(256), 0, st, in, out, Ho, Wo, total, adjoint ? 1 : 0);
+    return check_launch("k_pool2_planes");
 }
 
 size_t mg_colsum_workspace_bytes(int C) {

@@ -336,3 +336,25 @@ class Unpool2(Function):
     @staticmethod
     def backward(ctx, gg):
         return Pool2.apply(gg)
+
+
+class PoolPlanes(Function):
+    """AvgPool2d(2, 2) on the fp32 NCHW network input (fade-in path of the discriminator); backward = UnpoolPlanes."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.pool2_planes(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return UnpoolPlanes.apply(g)
+
+
+class UnpoolPlanes(Function):
+    @staticmethod
+    def forward(ctx, g):
+        return ops.pool2_planes(g, adjoint=True)
+
+    @staticmethod
+    def backward(ctx, gg):
+        return PoolPlanes.apply(gg)

@@ -53,6 +53,7 @@ def _l():
         l.mg_pixelnorm_lrelu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int64, c_int, c_void_p]
         l.mg_lrelu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int64, c_int, c_void_p]
         l.mg_unpool2_lrelu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]
+        l.mg_pool2_planes_f32.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]
         l.mg_conv3x3_pack_weights.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]
         _declared = True
     return l
@@ -314,3 +315,21 @@ def unpool_lrelu_bwd(gp: th.Tensor, h: th.Tensor, want_bias_grad: bool = True):
                                                ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
                                                B, H // 2, W // 2, C, _stream()), "mg_unpool2_lrelu_bwd_bf16")
     return gz, gb
+
+
+def pool2_planes(x: th.Tensor, adjoint: bool = False) -> th.Tensor:
+    """AvgPool2d(2, 2) of fp32 NCHW planes (B, C, H, W) -> (B, C, H/2, W/2), or (adjoint) its backward
+    (B, C, H, W) -> (B, C, 2H, 2W) = 0.25 * x replicated.  Same bits as torch's avg_pool2d / avg_pool2d_backward."""
+    x = _planes(x, "pool2_planes x")
+    B, C, H, W = x.shape
+    if adjoint:
+        out = th.empty((B, C, 2 * H, 2 * W), dtype=th.float32, device=x.device)
+        ho, wo = H, W
+    else:
+        assert H % 2 == 0 and W % 2 == 0
+        ho, wo = H // 2, W // 2
+        out = th.empty((B, C, ho, wo), dtype=th.float32, device=x.device)
+    with th.cuda.device(x.device):
+        _lib.check(_l().mg_pool2_planes_f32(x.data_ptr(), out.data_ptr(), B * C, ho, wo, 1 if adjoint else 0, _stream()),
+                   "mg_pool2_planes_f32")
+    return out

@@ -212,3 +212,22 @@ def test_unpool_lrelu_backward_kernel(B, C, H, W):
     assert torch.allclose(gb, exact, rtol=1e-4, atol=1e-4 * exact.abs().max().item())
     gz2, none = ops.unpool_lrelu_bwd(gp, h, want_bias_grad=False)
     assert none is None and torch.equal(gz2, gz_ref)
+
+
+def test_pool2_planes_matches_torch_bitwise():
+    """mg_pool2_planes_f32 (fp32 NCHW input planes of the fade-in path) == F.avg_pool2d and its backward, bit for bit,
+    including through autograd (double backward = the pooling again)."""
+    from musicgan_b200.networks import ops, functional as fn
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(3, 2, 64, 48, generator=g).cuda()
+    assert torch.equal(ops.pool2_planes(x), F.avg_pool2d(x, 2, 2))
+    gsmall = torch.randn(3, 2, 32, 24, generator=g).cuda()
+    xr = x.clone().requires_grad_(True)
+    ref = torch.autograd.grad(F.avg_pool2d(xr, 2, 2), xr, gsmall)[0]
+    assert torch.equal(ops.pool2_planes(gsmall, adjoint=True), ref)
+    xa = x.clone().requires_grad_(True)
+    got = torch.autograd.grad(fn.PoolPlanes.apply(xa), xa, gsmall, create_graph=True)[0]
+    assert torch.equal(got, ref)
+    gs2 = gsmall.clone().requires_grad_(True)
+    gg = torch.autograd.grad(fn.UnpoolPlanes.apply(gs2), gs2, x)[0]
+    assert torch.equal(gg, F.avg_pool2d(x, 2, 2))
