@@ -147,13 +147,18 @@ def cpu_transform_baseline(seconds: float = 10.0):
     return frames / el, n, el
 
 
+def synthetic_wavs(batch: int, n: int, seed: int) -> torch.Tensor:
+    """(batch, n) mono uniform-noise clips in [-0.5, 0.5) (the product arm imports nothing from oracle/)."""
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(batch, n, generator=g) * 2 - 1) * 0.5
+
+
 def run_transform(args, rank, world, local):
     from musicgan_b200 import _lib, audio
-    from oracle import cases
     clips = args.clips
     plan = audio.ForwardPlan(N_60S, clips, 1)
     frames_per_step = clips * plan.T
-    host = cases.batch_wavs(clips, N_60S, seed=2024 + rank).pin_memory()
+    host = synthetic_wavs(clips, N_60S, seed=2024 + rank).pin_memory()
     dev = host.cuda(non_blocking=True)
     torch.cuda.synchronize()
 
