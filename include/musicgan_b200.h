@@ -122,14 +122,28 @@ int mg_istft_from_magif_f32(const float* magn_phase, int n_clips, int imgs_per_c
  * x [B][H(/2)][W(/2)][Cin] bf16, y [B][H][W][Cout] bf16; H, W are the OUTPUT dims.
  * flags: 1 = LeakyReLU(0.2) epilogue, 2 = PixelNorm epilogue (writes inv_norm [B][H][W] fp32 if non-null),
  *        4 = input is read through a nearest x2 upsampling, 8 = data-gradient mode: `w_f32` is still the
- *        forward weight [Cfwd_out = Cin][Cfwd_in = Cout][3][3] and y = dL/dx of the forward conv for x = dL/dy.
+ *        forward weight [Cfwd_out = Cin][Cfwd_in = Cout][3][3] and y = dL/dx of the forward conv for x = dL/dy,
+ *        16 = weights enter as hi + lo bf16 pairs (w = bf16(w) + bf16(w - bf16(w)), two MMA sweeps per tile): used by
+ *        the forward convolutions, whose pre-activation SIGNS decide the LeakyReLU masks of the whole backward pass.
  * ---------------------------------------------------------------------------------------- */
 size_t mg_conv3x3_workspace_bytes(int Cin, int Cout);
 /* Pack fp32 weights once (e.g. per optimiser step) into `packed` (>= mg_conv3x3_workspace_bytes); mg_conv3x3_bf16
- * called with w_f32 == NULL then reads its `ws` argument as such a pre-packed buffer (same Cin, Cout, dgrad). */
-int mg_conv3x3_pack_weights(const float* w_f32, int Cin, int Cout, int dgrad, void* packed, size_t packed_bytes, mgStream stream);
+ * called with w_f32 == NULL then reads its `ws` argument as such a pre-packed buffer (same Cin, Cout and mode).
+ * mode: bit 0 data-gradient orientation (flag 8), bit 1 hi + lo pairs (flag 16), bit 2 the layer runs with flag 2. */
+int mg_conv3x3_pack_weights(const float* w_f32, int Cin, int Cout, int mode, void* packed, size_t packed_bytes, mgStream stream);
 int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* y, float* inv_norm,
                     int B, int H, int W, int Cin, int Cout, int flags, void* ws, size_t ws_bytes, mgStream stream);
+
+/* The same convolution on fp32 NHWC activations with split-bf16 operands (x = hi + lo, w = hi + lo, three MMAs per
+ * K step: ~16 significand bits): the precise path of the layers whose output height is <= 32, where bf16 operand
+ * rounding flips LeakyReLU masks and moves the WGAN-GP gradients by several percent (conv_split.cu).
+ * x [B][H(/2)][W(/2)][Cin] fp32, y [B][H][W][Cout] fp32, y_bf16 optional bf16 copy of y (operand of
+ * mg_conv3x3_wgrad_bf16), `packed` from mg_conv3x3_split_pack_weights (>= mg_conv3x3_split_workspace_bytes; dgrad != 0
+ * packs the data-gradient orientation, to be used with flag 8).  flags 1, 2, 4, 8 as mg_conv3x3_bf16. */
+size_t mg_conv3x3_split_workspace_bytes(int Cin, int Cout);
+int mg_conv3x3_split_pack_weights(const float* w_f32, int Cin, int Cout, int dgrad, void* packed, size_t packed_bytes, mgStream stream);
+int mg_conv3x3_split_f32(const float* x, const void* packed, const float* bias, float* y, void* y_bf16, float* inv_norm,
+                         int B, int H, int W, int Cin, int Cout, int flags, mgStream stream);
 
 /* Weight gradient of the same convolution: dw[co][ci][ky][kx] = sum_{b,y,x} dy[b][y][x][co] *
  * xin[b][y+ky-1][x+kx-1][ci]   (xin = x, or x read through a nearest x2 upsampling when upsample_in != 0).
@@ -197,6 +211,21 @@ int mg_debug_umma_gemm(const void* A, const void* B, float* D, int K, int N, int
  * shape 0: 16x64b.x1, 1: 16x128b.x1, 2: 16x128b.x2, 3: 16x256b.x1 by warp 0 with register values
  * 0x1000 | thread << 4 | (register index + 1); out [128 lanes][32 columns] uint32 = the TMEM block afterwards. */
 int mg_debug_tmem_store(uint32_t* out, int shape, int lane_off, int col_off, mgStream stream);
+
+/* The same memory-bound layers on fp32 NHWC activations (precise path of the low-resolution layers; same arguments,
+ * every `void*` activation / mask tensor is fp32 instead of bf16). */
+int mg_rgb_expand_f32(const float* x, const float* w, const float* b, const void* mask_src, void* y,
+                      int B, int64_t HW, int C, int mode, mgStream stream);
+int mg_rgb_project_f32(const void* a, const float* w2, int row_stride, int col_stride, const float* bias, const void* mask_src,
+                       float* out, int B, int64_t HW, int C, int act, mgStream stream);
+int mg_rgb_wgrad_f32(const void* g, const void* mask_src, const float* x, float* gw, float* gb, int B, int64_t HW, int C, mgStream stream);
+int mg_pool2_f32(const void* in, void* out, int B, int Ho, int Wo, int C, int adjoint, mgStream stream);
+int mg_lrelu_bwd_f32(const void* gy, const void* y, void* gz, float* gb, void* ws, size_t ws_bytes,
+                     int64_t n_pixels, int C, mgStream stream);
+int mg_unpool2_lrelu_bwd_f32(const void* gp, const void* h, void* gz, float* gb, void* ws, size_t ws_bytes,
+                             int B, int Hi, int Wi, int C, mgStream stream);
+int mg_pixelnorm_lrelu_bwd_f32(const void* go, const void* o, const float* inv_norm, void* gz, float* gb, void* ws, size_t ws_bytes,
+                               int64_t n_pixels, int C, mgStream stream);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,7 @@ struct ConvParams {
     int consumer_fence;
     int ablate;                  // debug (MG_CONV_ABLATE): 1 no halo copies, 2 no MMAs, 4 no epilogue work, 8 no global stores
     int epi_warps;               // 4 or 8 epilogue warps; producers are the next 4 warps, then the MMA warp
+    int parts;                   // 1: bf16 weights; 2: weights as hi + lo bf16 pairs, two MMA sweeps over the same halo
 };
 
 // warp roles: [0, E) epilogue (E = 4, or 8 = two per TMEM lane quarter with half the columns each), [E, E+4) producers,
@@ -75,8 +76,8 @@ k_conv3x3(const ConvParams p) {
     const int nt = min(p.Nt, p.Cout - n0);
     const int kEpiWarps = p.epi_warps, kProdWarp0 = kEpiWarps, kMmaWarp = kEpiWarps + 4;
 
-    uint4* sW = reinterpret_cast<uint4*>(smem);                    // [9 taps][nch][nt] + bias pseudo-tap [2][nt]
-    uint4* sOnes = sW + (9 * nch + 2) * nt;                        // [2][128]: the constant A tile of the bias MMA
+    uint4* sW = reinterpret_cast<uint4*>(smem);                    // [parts][9 taps][nch][nt] + bias pseudo-tap [2][nt]
+    uint4* sOnes = sW + (9 * nch * p.parts + 2) * nt;              // [2][128]: the constant A tile of the bias MMA
     uint4* sA0 = sOnes + 256;
     float* sPart = reinterpret_cast<float*>(sA0 + (size_t)p.stages * nch * p.halo_pitch);      // [2][128] PixelNorm partial sums
     uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + 256);
@@ -111,14 +112,14 @@ k_conv3x3(const ConvParams p) {
         // ================= producers =================
         const int pt = tid - kProdWarp0 * 32;
         {   // resident weights of this slice + bias
-            const uint4* src = p.wpack + (size_t)9 * nch * n0;
-            const int total = 9 * nch * nt;
+            const uint4* src = p.wpack + (size_t)9 * nch * n0 * p.parts;
+            const int total = 9 * nch * nt * p.parts;
             // all chunks in flight at once (the deep layers carry up to 140 KB of weights per slice: a synchronous
             // load loop here used to dominate the run time of the small-spatial layers)
             const uint32_t sw_addr = smem_u32(sW);
             for (int i = pt; i < total; i += 128) cp_async16(sw_addr + (uint32_t)i * 16u, src + i, 16u);
             if (kBA) {
-                uint4* sB = sW + 9 * nch * nt;
+                uint4* sB = sW + 9 * nch * nt * p.parts;
                 for (int i = pt; i < nt; i += 128) {
                     const float bv = p.bias ? p.bias[n0 + i] : 0.0f;
                     const __nv_bfloat16 hi = __float2bfloat16_rn(bv), lo = __float2bfloat16_rn(bv - __bfloat162float(hi));
@@ -220,15 +221,20 @@ k_conv3x3(const ConvParams p) {
                     const uint64_t da_blk = a_desc0 + (uint64_t)(slot * slot_units + blk * (kTileH * kHaloW));
                     uint64_t db = b_desc0;
                     uint32_t accum = 0;
+                    // parts == 2: a second sweep of the same halo against the low halves of the weights (w = hi + lo:
+                    // 16 significand bits, so that LeakyReLU masks agree with the fp32 reference's; the tensor pipe is
+                    // far from saturated on these HBM-bound layers)
                     if (!(p.ablate & 2))
+                    for (int part = 0; part < p.parts; ++part) {
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        uint64_t da = da_blk + (uint64_t)((tap / 3) * kHaloW + (tap % 3));
-                        for (int kk = 0; kk < ksteps; ++kk) {
-                            mma_bf16(d, da, db, idesc, accum);
-                            accum = 1;
-                            da += a_kstep;
-                            db += b_step;
+                        for (int tap = 0; tap < 9; ++tap) {
+                            uint64_t da = da_blk + (uint64_t)((tap / 3) * kHaloW + (tap % 3));
+                            for (int kk = 0; kk < ksteps; ++kk) {
+                                mma_bf16(d, da, db, idesc, accum);
+                                accum = 1;
+                                da += a_kstep;
+                                db += b_step;
+                            }
                         }
                     }
                     if (kBA) mma_bf16(d, ones_desc, db, idesc, 1u);      // + bias (db now points at the bias pseudo-tap)
@@ -346,13 +352,14 @@ k_conv3x3(const ConvParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight packing: fp32 [Cout][Cin][3][3]  ->  bf16 [slice][tap][Cin/8][nt][8]
+// weight packing: fp32 [Cout][Cin][3][3]  ->  bf16 [slice][part][tap][Cin/8][nt][8]   (part 0 = bf16(w), part 1 =
+// bf16(w - part 0) when parts == 2)
 //   transpose_flip = 0 (fprop):  B[n = co][k = ci] of tap (ky,kx) = w[co][ci][ky][kx]
 //   transpose_flip = 1 (dgrad):  the data gradient is a 3x3 convolution of dY with
 //                                w'[ci][co][ky][kx] = w[co][ci][2-ky][2-kx]; n runs over ci, k over co.
 //   `n_out`, `k_in` are the GEMM N and K channel counts of the packed operand.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_pack_weights(const float* __restrict__ w, int Cout, int Cin, int transpose_flip, int Nt,
+__global__ void k_pack_weights(const float* __restrict__ w, int Cout, int Cin, int transpose_flip, int Nt, int parts,
                                __nv_bfloat16* __restrict__ out) {
     const int n_out = transpose_flip ? Cin : Cout, k_in = transpose_flip ? Cout : Cin;
     const int nch = k_in >> 3;
@@ -377,7 +384,10 @@ __global__ void k_pack_weights(const float* __restrict__ w, int Cout, int Cin, i
                 float v;
                 if (!transpose_flip) v = w[(((size_t)n * Cin + k) * 3 + ky) * 3 + kx];
                 else v = w[(((size_t)k * Cin + n) * 3 + (2 - ky)) * 3 + (2 - kx)];
-                out[i] = __float2bfloat16_rn(v);
+                const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                // slice base in the output is parts * base; part 1 follows the cnt elements of part 0
+                out[(size_t)parts * base * 8 + (size_t)q * 8 + e] = hi;
+                if (parts == 2) out[(size_t)parts * base * 8 + (size_t)cnt * 8 + (size_t)q * 8 + e] = __float2bfloat16_rn(v - __bfloat162float(hi));
                 break;
             }
             base += cnt; ++slice;
@@ -387,8 +397,10 @@ __global__ void k_pack_weights(const float* __restrict__ w, int Cout, int Cin, i
 
 struct ConvPlan { int Nt, stages, tmem_cols, n_slices, occupancy, epi_warps, n_acc, acc_stride, mb, blk_stride, halo_pos, halo_pitch; size_t smem; };
 
-static ConvPlan plan_conv(int Cin, int Cout, bool need_full_n, int H = 0) {
-    const size_t budget = 200 * 1024;
+static ConvPlan plan_conv(int Cin, int Cout, bool need_full_n, int H = 0, int parts = 1) {
+    // hi + lo weights (parts == 2) double the resident weights: the PixelNorm layers (full N per CTA) then need the
+    // whole 227 KB of a CTA and run with one or two halo slots
+    const size_t budget = (parts == 2 && need_full_n ? 224 : 200) * 1024;
     const int nch = Cin / 8;
     ConvPlan pl{};
     // 1. N slice: the widest slice whose resident weights leave room for two single-block halo slots (one if need be).
@@ -396,9 +408,9 @@ static ConvPlan plan_conv(int Cin, int Cout, bool need_full_n, int H = 0) {
     int Nt = 0;
     for (int stages = 2; stages >= 1 && !Nt; --stages)
         for (int n = Cout; n >= 16; n -= 16)
-            if ((size_t)9 * nch * n * 16 + (size_t)stages * nch * kHaloPitch * 16 + (size_t)2 * n * 16 + 4096 + 1024 + 384 <= budget) { Nt = n; break; }
+            if ((size_t)9 * nch * n * 16 * parts + (size_t)stages * nch * kHaloPitch * 16 + (size_t)2 * n * 16 + 4096 + 1024 + 384 <= budget) { Nt = n; break; }
     if (!Nt || (need_full_n && Nt != Cout)) return pl;
-    const size_t base = (size_t)9 * nch * Nt * 16 + (size_t)2 * Nt * 16 + 4096 + 1024 + 384;   // weights, bias pseudo-tap, constant A tile, PixelNorm partials, barriers
+    const size_t base = (size_t)9 * nch * Nt * 16 * parts + (size_t)2 * Nt * 16 + 4096 + 1024 + 384;   // weights, bias pseudo-tap, constant A tile, PixelNorm partials, barriers
     // 2. shape of one pipeline step.  The warps of a CTA are few and specialised, so (a) several CTAs share an SM
     //    (registers: 72/thread -> 3 CTAs of 9 warps with 4 epilogue warps, or 2 CTAs of 13 warps with 8) and (b) on
     //    the large images a step covers `mb` vertically stacked 16 x 8 blocks, which divides the per-step costs
@@ -448,25 +460,29 @@ using namespace mg;
 
 extern "C" {
 
-int mg_conv3x3_pack_weights(const float* w_f32, int Cin, int Cout, int dgrad, void* packed, size_t packed_bytes, mgStream stream) {
+// mode: bit 0 = data-gradient orientation, bit 1 = hi + lo pairs (for mg_conv3x3_bf16 with flag 16), bit 2 = the layer
+// runs with the PixelNorm epilogue (all output channels in one slice: the slice width is part of the packed layout)
+int mg_conv3x3_pack_weights(const float* w_f32, int Cin, int Cout, int mode, void* packed, size_t packed_bytes, mgStream stream) {
     if (!w_f32 || !packed) return MG_ERR_BAD_ARG;
     if (Cin < 16 || Cout < 16 || (Cin & 15) || (Cout & 15) || Cin > 256 || Cout > 256) return MG_ERR_UNSUPPORTED;
-    if (packed_bytes < (size_t)9 * Cin * Cout * 2) return MG_ERR_WORKSPACE;
-    ConvPlan pl = plan_conv(Cin, Cout, false);
+    const int dgrad = mode & 1, parts = (mode & 2) ? 2 : 1;
+    if (packed_bytes < (size_t)9 * Cin * Cout * 2 * parts) return MG_ERR_WORKSPACE;
+    ConvPlan pl = plan_conv(Cin, Cout, (mode & 4) != 0, 0, parts);
     if (pl.Nt == 0) return MG_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope ps("k_pack_weights", st);
     const int total = 9 * Cin * Cout;
     const int fwd_cout = dgrad ? Cin : Cout, fwd_cin = dgrad ? Cout : Cin;
-    launch_pdl(k_pack_weights, dim3((total + 255) / 256), dim3(256), 0, st, w_f32, fwd_cout, fwd_cin, dgrad ? 1 : 0, pl.Nt, (__nv_bfloat16*)packed);
+    launch_pdl(k_pack_weights, dim3((total + 255) / 256), dim3(256), 0, st, w_f32, fwd_cout, fwd_cin, dgrad ? 1 : 0, pl.Nt, parts, (__nv_bfloat16*)packed);
     return check_launch("k_pack_weights");
 }
 
 size_t mg_conv3x3_workspace_bytes(int Cin, int Cout) {
-    return align_up((size_t)9 * Cin * Cout * 2, 256);
+    return align_up((size_t)9 * Cin * Cout * 4, 256);       // room for the hi + lo packing
 }
 
-// flags: bit0 LeakyReLU(0.2), bit1 PixelNorm, bit2 input is nearest-upsampled x2 on the fly, bit3 dgrad weights
+// flags: bit0 LeakyReLU(0.2), bit1 PixelNorm, bit2 input is nearest-upsampled x2 on the fly, bit3 dgrad weights,
+// bit4 weights as hi + lo bf16 pairs (two MMA sweeps)
 int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* y, float* inv_norm,
                     int B, int H, int W, int Cin, int Cout, int flags, void* ws, size_t ws_bytes, mgStream stream) {
     if (!x || !y || !ws) return MG_ERR_BAD_ARG;      // w_f32 == NULL: `ws` already holds the packed weights
@@ -477,7 +493,8 @@ int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* 
     if (ups && ((H | W) & 1)) return MG_ERR_BAD_ARG;
     if (ws_bytes < mg_conv3x3_workspace_bytes(Cin, Cout)) return MG_ERR_WORKSPACE;
     const bool pn = (flags & 2) != 0;
-    ConvPlan pl = plan_conv(Cin, Cout, pn, H);
+    const int parts = (flags & 16) ? 2 : 1;
+    ConvPlan pl = plan_conv(Cin, Cout, pn, H, parts);
     if (pl.Nt == 0) return MG_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     if (w_f32) {
@@ -486,14 +503,14 @@ int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* 
         // w_f32 is [Cout_w][Cin_w][3][3] of the FORWARD convolution; for dgrad the GEMM's K (=Cin here) is the
         // forward Cout and the GEMM's N (=Cout here) the forward Cin
         const int fwd_cout = dgrad ? Cin : Cout, fwd_cin = dgrad ? Cout : Cin;
-        launch_pdl(k_pack_weights, dim3((total + 255) / 256), dim3(256), 0, st, w_f32, fwd_cout, fwd_cin, dgrad ? 1 : 0, pl.Nt, (__nv_bfloat16*)ws);
+        launch_pdl(k_pack_weights, dim3((total + 255) / 256), dim3(256), 0, st, w_f32, fwd_cout, fwd_cin, dgrad ? 1 : 0, pl.Nt, parts, (__nv_bfloat16*)ws);
     }
     ConvParams p{};
     p.x = (const __nv_bfloat16*)x; p.wpack = (const uint4*)ws; p.bias = bias; p.y = (__nv_bfloat16*)y; p.inv_norm = inv_norm;
     p.B = B; p.H = H; p.W = W; p.Hin = ups ? H / 2 : H; p.Win = ups ? W / 2 : W; p.Cin = Cin; p.Cout = Cout;
     p.upsample = ups; p.lrelu = flags & 1; p.pixelnorm = pn;
     p.tiles_x = (W + kTileW - 1) / kTileW; p.tiles_y = (H + kTileH * pl.mb - 1) / (kTileH * pl.mb); p.n_tiles = B * p.tiles_x * p.tiles_y;
-    p.Nt = pl.Nt; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols; p.epi_warps = pl.epi_warps;
+    p.Nt = pl.Nt; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols; p.epi_warps = pl.epi_warps; p.parts = parts;
     p.n_acc = pl.n_acc; p.acc_stride = pl.acc_stride; p.mb = pl.mb; p.blk_stride = pl.blk_stride;
     p.halo_pos = pl.halo_pos; p.halo_pitch = pl.halo_pitch;
     p.idiv = make_item_div(Cin / 8);

@@ -120,8 +120,10 @@ class GraphedSteps:
     def critic_step(self, x_real: th.Tensor) -> th.Tensor:
         self.x_real.copy_(x_real, non_blocking=True)
         self._gd.replay()
+        ops.invalidate_pack_cache()      # the optimiser step inside the graph fires no hook: packed weights are stale now
         return self.d_stats          # [d_loss, grad_pen, mean D(real), mean D(fake)] (device tensor, overwritten on replay)
 
     def generator_step(self) -> th.Tensor:
         self._gg.replay()
+        ops.invalidate_pack_cache()
         return self.g_stats          # [g_loss, mean D(fake)]

@@ -8,7 +8,9 @@ penalty, reference networks/discriminator.py:157-184) works through them:
     dgrad(g, w)  = conv3x3_transposed(g, w)           d/dg -> fprop(gg, w)   d/dw -> wgrad(g, gg)
     wgrad(g, x)  = sum_pixels g (x) shifted x         d/dg -> fprop(x, gw)   d/dx -> dgrad(g, gw)
 
-Activations: bf16, channels_last.  Weights / weight gradients: fp32.
+Activations: channels_last; bf16 on the layers above 32 x 32, fp32 on the low-resolution layers (the precise path,
+split-bf16 operands: ops.PRECISE_MAX_RES, conv_split.cu).  Every function follows the dtype of the activation it is given;
+the modules (progan.py) choose it per layer with `prep`.  Weights / weight gradients: fp32.
 """
 from __future__ import annotations
 
@@ -25,7 +27,13 @@ PN_EPS = 1e-8
 
 
 def _act(t: th.Tensor) -> th.Tensor:
-    return ops.as_act(t)
+    return ops.keep_act(t)
+
+
+def prep(x: th.Tensor, h_out: int) -> th.Tensor:
+    """Input of a layer whose output height is `h_out`, in the activation dtype that layer runs in (a differentiable
+    cast where a bf16 layer feeds a precise one or vice versa)."""
+    return ops.as_act(x, th.float32 if ops.is_precise(h_out) else th.bfloat16)
 
 
 # ctx.needs_input_grad is fixed when the forward runs (does the INPUT require grad?), it does not know which
@@ -106,7 +114,7 @@ class ConvBiasLReLU(Function):
 
     @staticmethod
     def forward(ctx, x, w, b):
-        y = ops.conv3x3(_act(x), w.float().contiguous(), b.float().contiguous(), lrelu=True)
+        y = ops.conv3x3(_act(x), w.float().contiguous(), b.float().contiguous(), lrelu=True, split_w=True)
         ctx.save_for_backward(x, w, y)
         return y
 
@@ -144,7 +152,7 @@ class LReLUBwd(Function):
         g = ggb.float()[None, :, None, None].expand(y.shape)
         if ggz is not None:
             g = g + ggz.float()
-        return (_act(g) * _lrelu_mask(y)), None, None
+        return (ops.as_act(g, y.dtype) * _lrelu_mask(y)), None, None
 
 
 class UnpoolLReLUBwd(Function):
@@ -167,7 +175,7 @@ class UnpoolLReLUBwd(Function):
         g = ggb.float()[None, :, None, None].expand(h.shape)
         if ggz is not None:
             g = g + ggz.float()
-        return Pool2.apply(_act(g) * _lrelu_mask(h)), None, None
+        return Pool2.apply(ops.as_act(g, h.dtype) * _lrelu_mask(h)), None, None
 
 
 class ConvBiasLReLUPool(Function):
@@ -177,7 +185,7 @@ class ConvBiasLReLUPool(Function):
 
     @staticmethod
     def forward(ctx, x, w, b):
-        h = ops.conv3x3(_act(x), w.float().contiguous(), b.float().contiguous(), lrelu=True)
+        h = ops.conv3x3(_act(x), w.float().contiguous(), b.float().contiguous(), lrelu=True, split_w=True)
         ctx.save_for_backward(x, w, h)
         return ops.pool2(h)
 
@@ -198,15 +206,17 @@ class GenConv(Function):
     @staticmethod
     def forward(ctx, x, w, b, upsample_in: bool):
         cout, cin = w.shape[0], w.shape[1]
-        fused_pn = 9 * cin * cout * 2 <= 120 * 1024      # weights of all Cout resident in smem (conv_igemm.cu plan)
         xa = _act(x)
+        # PixelNorm needs all Cout of a pixel in one CTA: the precise kernel streams its weights (Cout <= 128), the
+        # bf16 kernel keeps them (hi + lo) resident in shared memory
+        fused_pn = cout <= 128 if xa.dtype == th.float32 else 9 * cin * cout * 4 <= 184 * 1024
         wf, bf = w.float().contiguous(), b.float().contiguous()
         if fused_pn:
-            o, inv = ops.conv3x3(xa, wf, bf, lrelu=True, pixelnorm=True, upsample_in=upsample_in, want_inv_norm=True)
-        else:
-            t = ops.conv3x3(xa, wf, bf, lrelu=True, upsample_in=upsample_in).float()
+            o, inv = ops.conv3x3(xa, wf, bf, lrelu=True, pixelnorm=True, upsample_in=upsample_in, want_inv_norm=True, split_w=True)
+        else:                # not reached by the reference's channel plan (generator.py:67-76)
+            t = ops.conv3x3(xa, wf, bf, lrelu=True, upsample_in=upsample_in, split_w=True).float()
             inv = th.rsqrt(t.pow(2).mean(dim=1) + PN_EPS)
-            o = _act(t * inv[:, None])
+            o = ops.as_act(t * inv[:, None], xa.dtype)
         ctx.save_for_backward(xa, w, o, inv)
         ctx.upsample_in = upsample_in
         return o
@@ -234,8 +244,8 @@ class RgbExpand(Function):
     One of the three mutually-differentiating 1x1 maps (RgbExpand / RgbProject / RgbWgrad)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, mask_src, lrelu: bool):
-        y = ops.rgb_expand(x, w, b, mask_src=mask_src, lrelu=lrelu)
+    def forward(ctx, x, w, b, mask_src, lrelu: bool, out_dtype=th.bfloat16):
+        y = ops.rgb_expand(x, w, b, mask_src=mask_src, lrelu=lrelu, out_dtype=out_dtype)
         ctx.save_for_backward(x, w, y if lrelu else mask_src)
         ctx.has_mask = lrelu or mask_src is not None
         ctx.w_shape = w.shape
@@ -250,7 +260,7 @@ class RgbExpand(Function):
         if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and _param_grads[0]:
             gw, gb = RgbWgrad.apply(gy, m, x)
             gw = gw.reshape(ctx.w_shape)
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
 class RgbProject(Function):
@@ -265,7 +275,7 @@ class RgbProject(Function):
     @staticmethod
     def backward(ctx, gout):
         a, w, m = ctx.saved_tensors
-        ga = RgbExpand.apply(gout, w, None, m, False) if ctx.needs_input_grad[0] else None
+        ga = RgbExpand.apply(gout, w, None, m, False, a.dtype) if ctx.needs_input_grad[0] else None
         gw = None
         if ctx.needs_input_grad[1] and _param_grads[0]:
             gw, _ = RgbWgrad.apply(a, m, gout)
@@ -284,7 +294,7 @@ class RgbWgrad(Function):
     @staticmethod
     def backward(ctx, ggw, ggb):
         g, m, x = ctx.saved_tensors
-        gg = RgbExpand.apply(x, ggw, ggb, m, False) if ctx.needs_input_grad[0] else None
+        gg = RgbExpand.apply(x, ggw, ggb, m, False, g.dtype) if ctx.needs_input_grad[0] else None
         gx = RgbProject.apply(g, ggw, m) if ctx.needs_input_grad[2] else None
         return gg, None, gx
 
@@ -307,7 +317,7 @@ class ToRgbTanh(Function):
         ga = gw = gb = None
         C = aa.shape[1]
         if ctx.needs_input_grad[0]:
-            ga = ops.rgb_expand(gpre, w.float().reshape(2, C).t().contiguous())
+            ga = ops.rgb_expand(gpre, w.float().reshape(2, C).t().contiguous(), out_dtype=aa.dtype)
         if ctx.needs_input_grad[1]:
             gwt, _ = ops.rgb_wgrad(aa, None, gpre)          # (C, 2)
             gw = gwt.t().reshape(w.shape).contiguous()

@@ -13,7 +13,18 @@ import torch as th
 
 from .. import _lib
 
-FLAG_LRELU, FLAG_PIXELNORM, FLAG_UPSAMPLE_IN, FLAG_DGRAD = 1, 2, 4, 8
+FLAG_LRELU, FLAG_PIXELNORM, FLAG_UPSAMPLE_IN, FLAG_DGRAD, FLAG_SPLIT_W = 1, 2, 4, 8, 16
+
+# Layers whose OUTPUT height is <= PRECISE_MAX_RES run on fp32 activations with split-bf16 operands (conv_split.cu): on
+# those few-pixel layers bf16 operand rounding flips LeakyReLU masks and moves the WGAN-GP gradients by 2-10 %
+# (scripts/precision_study.py; north_star asks for 1e-2).  0 switches the precise path off.
+PRECISE_MAX_RES = int(os.environ.get("MG_PRECISE_MAX_RES", "32"))
+# Forward convolutions of the bf16 layers take their weights as hi + lo bf16 pairs (flag 16); 0 = plain bf16 weights.
+SPLIT_W = os.environ.get("MG_SPLIT_W", "1") != "0"
+
+
+def is_precise(h_out: int) -> bool:
+    return h_out <= PRECISE_MAX_RES
 
 _declared = False
 _ws_cache = {}
@@ -55,6 +66,18 @@ def _l():
         l.mg_unpool2_lrelu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]
         l.mg_pool2_planes_f32.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]
         l.mg_conv3x3_pack_weights.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]
+        l.mg_conv3x3_split_workspace_bytes.restype = c_size_t
+        l.mg_conv3x3_split_workspace_bytes.argtypes = [c_int, c_int]
+        l.mg_conv3x3_split_pack_weights.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]
+        l.mg_conv3x3_split_f32.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]
+        for sfx in ("_f32",):
+            getattr(l, "mg_rgb_expand" + sfx).argtypes = l.mg_rgb_expand_bf16.argtypes
+            getattr(l, "mg_rgb_project" + sfx).argtypes = l.mg_rgb_project_bf16.argtypes
+            getattr(l, "mg_rgb_wgrad" + sfx).argtypes = l.mg_rgb_wgrad_bf16.argtypes
+            getattr(l, "mg_pool2" + sfx).argtypes = l.mg_pool2_bf16.argtypes
+            getattr(l, "mg_lrelu_bwd" + sfx).argtypes = l.mg_lrelu_bwd_bf16.argtypes
+            getattr(l, "mg_unpool2_lrelu_bwd" + sfx).argtypes = l.mg_unpool2_lrelu_bwd_bf16.argtypes
+            getattr(l, "mg_pixelnorm_lrelu_bwd" + sfx).argtypes = l.mg_pixelnorm_lrelu_bwd_bf16.argtypes
         _declared = True
     return l
 
@@ -86,11 +109,13 @@ except ImportError:      # pragma: no cover  (older torch: train_step invalidate
     pass
 
 
-def _packed_weights(w: th.Tensor, cin: int, cout: int, dgrad: bool):
-    """Packed bf16 copy of a weight tensor, cached ON the parameter object per (version, storage address): parameters
-    change once per optimiser step but are read by several forward / backward kernels.  The cache lives and dies with
-    the Parameter (a global dict keyed by address would hand one model's weights to the next model allocated at the
-    same address).  Temporaries (double-backward operands) are never cached."""
+def _packed_weights(w: th.Tensor, cin: int, cout: int, kind):
+    """Packed copy of a weight tensor, cached ON the parameter object per (version, storage address): parameters change
+    once per optimiser step but are read by several forward / backward kernels.  `kind` = ("bf16", mode) with the mode
+    bits of mg_conv3x3_pack_weights (1 dgrad, 2 hi + lo, 4 PixelNorm layer) or ("split", dgrad) for conv_split.cu;
+    cin / cout are those of the GEMM that will run.  The cache lives and dies with the Parameter (a global dict keyed by
+    address would hand one model's weights to the next model allocated at the same address).  Temporaries
+    (double-backward operands) are never cached."""
     if os.environ.get("MG_NO_PACK_CACHE") or not (w.is_leaf and w.requires_grad):
         return None
     cache = getattr(w, "_mg_packed", None)
@@ -98,46 +123,62 @@ def _packed_weights(w: th.Tensor, cin: int, cout: int, dgrad: bool):
         cache = {}
         w._mg_packed = cache
     stamp = (w._version, w.data_ptr(), _pack_epoch[0])
-    hit = cache.get(dgrad)
+    key = (kind, cin, cout)
+    hit = cache.get(key)
     if hit is not None and hit[0] == stamp:
         return hit[1]
     l = _l()
-    nbytes = l.mg_conv3x3_workspace_bytes(cin, cout)
+    split = kind[0] == "split"
+    nbytes = l.mg_conv3x3_split_workspace_bytes(cin, cout) if split else l.mg_conv3x3_workspace_bytes(cin, cout)
     buf = hit[1] if (hit is not None and hit[1].device == w.device) else th.empty(nbytes, dtype=th.uint8, device=w.device)
     with th.cuda.device(w.device):
-        _lib.check(l.mg_conv3x3_pack_weights(w.data_ptr(), cin, cout, 1 if dgrad else 0, buf.data_ptr(), buf.numel(),
-                                             th.cuda.current_stream().cuda_stream), "mg_conv3x3_pack_weights")
-    cache[dgrad] = (stamp, buf)
+        if split:
+            _lib.check(l.mg_conv3x3_split_pack_weights(w.data_ptr(), cin, cout, kind[1], buf.data_ptr(), buf.numel(),
+                                                       th.cuda.current_stream().cuda_stream), "mg_conv3x3_split_pack_weights")
+        else:
+            _lib.check(l.mg_conv3x3_pack_weights(w.data_ptr(), cin, cout, kind[1], buf.data_ptr(), buf.numel(),
+                                                 th.cuda.current_stream().cuda_stream), "mg_conv3x3_pack_weights")
+    cache[key] = (stamp, buf)
     return buf
 
 
 def prepack(module) -> None:
-    """Pack (or refresh) both orientations of every 3x3 weight of `module` on the current stream.  After this call the
-    forward / data-gradient kernels only READ the cached copies, so independent branches of a step may run on
-    different streams (graphed.py)."""
+    """Refresh, on the current stream, every packed copy the parameters of `module` have been asked for so far (the
+    warm-up steps before a graph capture ask for all of them).  After this call the forward / data-gradient kernels only
+    READ the cached copies, so independent branches of a step may run on different streams (graphed.py)."""
     for p in module.parameters():
-        if p.dim() == 4 and tuple(p.shape[2:]) == (3, 3) and p.is_cuda and p.requires_grad and p.dtype == th.float32:
-            cout, cin = p.shape[0], p.shape[1]
-            _packed_weights(p, cin, cout, False)
-            _packed_weights(p, cout, cin, True)
+        cache = getattr(p, "_mg_packed", None)
+        if cache and p.is_cuda and p.requires_grad:
+            for (kind, cin, cout) in list(cache.keys()):
+                _packed_weights(p, cin, cout, kind)
 
 
-def _check_act(x: th.Tensor, name: str):
-    if not (x.is_cuda and x.dtype == th.bfloat16 and x.dim() == 4):
-        raise TypeError(f"{name}: expected a CUDA bf16 (B, C, H, W) tensor, got {x.dtype} {tuple(x.shape)} on {x.device}")
+def _check_act(x: th.Tensor, name: str, dtype=None):
+    if not (x.is_cuda and x.dtype in (th.bfloat16, th.float32) and x.dim() == 4) or (dtype is not None and x.dtype != dtype):
+        raise TypeError(f"{name}: expected a CUDA {dtype or 'bf16 / fp32'} (B, C, H, W) tensor, got {x.dtype} {tuple(x.shape)} on {x.device}")
     if not x.is_contiguous(memory_format=th.channels_last):
         raise ValueError(f"{name}: activations must be channels_last (NHWC in memory)")
 
 
-def as_act(x: th.Tensor) -> th.Tensor:
-    """bf16 + channels_last (no copy if already so)."""
-    return x.to(dtype=th.bfloat16).contiguous(memory_format=th.channels_last)
+def as_act(x: th.Tensor, dtype=th.bfloat16) -> th.Tensor:
+    """`dtype` (bf16, or fp32 on the precise path) + channels_last (no copy if already so)."""
+    return x.to(dtype=dtype).contiguous(memory_format=th.channels_last)
+
+
+def keep_act(x: th.Tensor) -> th.Tensor:
+    """channels_last in the tensor's own activation dtype (fp32 stays fp32, everything else becomes bf16)."""
+    return as_act(x, th.float32 if x.dtype == th.float32 else th.bfloat16)
+
+
+def _sfx(x: th.Tensor) -> str:
+    return "_f32" if x.dtype == th.float32 else "_bf16"
 
 
 def conv3x3(x: th.Tensor, w: th.Tensor, bias=None, *, lrelu=False, pixelnorm=False, upsample_in=False,
-            dgrad=False, want_inv_norm=False):
+            dgrad=False, want_inv_norm=False, split_w=False):
     """y = conv3x3(x) (+bias) (+LeakyReLU 0.2) (+PixelNorm); `upsample_in` reads x through a nearest x2
-    upsampling; `dgrad` computes the data gradient of the forward conv with weight `w` for x = dL/dy."""
+    upsampling; `dgrad` computes the data gradient of the forward conv with weight `w` for x = dL/dy.
+    fp32 x -> the split-operand kernel (fp32 y); bf16 x -> the bf16 kernel (bf16 y), with hi + lo weights if `split_w`."""
     _check_act(x, "conv3x3 x")
     assert w.is_cuda and w.dtype == th.float32 and w.is_contiguous() and w.dim() == 4 and w.shape[2:] == (3, 3)
     B, C, Hin, Win = x.shape
@@ -148,19 +189,34 @@ def conv3x3(x: th.Tensor, w: th.Tensor, bias=None, *, lrelu=False, pixelnorm=Fal
     else:
         assert w.shape[1] == C, (w.shape, C)
         cin, cout = C, w.shape[0]
+    precise = x.dtype == th.float32
     flags = (FLAG_LRELU if lrelu else 0) | (FLAG_PIXELNORM if pixelnorm else 0) | \
-            (FLAG_UPSAMPLE_IN if upsample_in else 0) | (FLAG_DGRAD if dgrad else 0)
-    y = th.empty((B, cout, H, W), dtype=th.bfloat16, device=x.device, memory_format=th.channels_last)
+            (FLAG_UPSAMPLE_IN if upsample_in else 0) | (FLAG_DGRAD if dgrad else 0) | \
+            (FLAG_SPLIT_W if (split_w and SPLIT_W and not precise) else 0)
+    y = th.empty((B, cout, H, W), dtype=x.dtype, device=x.device, memory_format=th.channels_last)
     inv = th.empty((B, H, W), dtype=th.float32, device=x.device) if (pixelnorm and want_inv_norm) else None
     l = _l()
-    packed = _packed_weights(w, cin, cout, dgrad)
+    if bias is not None:
+        assert bias.dtype == th.float32 and bias.numel() == cout and bias.is_cuda
+    _account(2.0 * B * H * W * 9 * cin * cout, float(x.element_size()) * (x.numel() + y.numel()))
+    if precise:
+        kind = ("split", 1 if dgrad else 0)
+        packed = _packed_weights(w, cin, cout, kind)
+        with th.cuda.device(x.device):
+            if packed is None:
+                packed = _workspace(x.device, l.mg_conv3x3_split_workspace_bytes(cin, cout), "split_pack")
+                _lib.check(l.mg_conv3x3_split_pack_weights(w.data_ptr(), cin, cout, kind[1], packed.data_ptr(), packed.numel(),
+                                                           th.cuda.current_stream().cuda_stream), "mg_conv3x3_split_pack_weights")
+            _lib.check(l.mg_conv3x3_split_f32(x.data_ptr(), packed.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                              y.data_ptr(), None, inv.data_ptr() if inv is not None else None,
+                                              B, H, W, cin, cout, flags, th.cuda.current_stream().cuda_stream), "mg_conv3x3_split_f32")
+        return (y, inv) if want_inv_norm else y
+    mode = (1 if dgrad else 0) | (2 if flags & FLAG_SPLIT_W else 0) | (4 if pixelnorm else 0)
+    packed = _packed_weights(w, cin, cout, ("bf16", mode))
     if packed is not None:
         ws, w_ptr = packed, None
     else:
         ws, w_ptr = _workspace(x.device, l.mg_conv3x3_workspace_bytes(cin, cout)), w.data_ptr()
-    if bias is not None:
-        assert bias.dtype == th.float32 and bias.numel() == cout and bias.is_cuda
-    _account(2.0 * B * H * W * 9 * cin * cout, 2.0 * (x.numel() + y.numel()))
     with th.cuda.device(x.device):
         _lib.check(l.mg_conv3x3_bf16(x.data_ptr(), w_ptr, bias.data_ptr() if bias is not None else None,
                                      y.data_ptr(), inv.data_ptr() if inv is not None else None,
@@ -172,6 +228,8 @@ def conv3x3(x: th.Tensor, w: th.Tensor, bias=None, *, lrelu=False, pixelnorm=Fal
 def conv3x3_wgrad(dy: th.Tensor, x: th.Tensor, *, upsample_in=False) -> th.Tensor:
     """dw[co][ci][ky][kx] = sum_{b,y,x} dy[b,co,y,x] * xin[b,ci,y+ky-1,x+kx-1]  (fp32), xin = x or its nearest
     x2 upsampling."""
+    # terminal product (nothing propagates from it): bf16 operands are enough, also for the fp32 layers of the precise path
+    dy, x = as_act(dy), as_act(x)
     _check_act(dy, "wgrad dy"); _check_act(x, "wgrad x")
     B, cout, H, W = dy.shape
     cin = x.shape[1]
@@ -197,18 +255,20 @@ def _planes(x: th.Tensor, name: str) -> th.Tensor:
     return x.float().contiguous()
 
 
-def rgb_expand(x: th.Tensor, w: th.Tensor, b=None, mask_src=None, lrelu=False) -> th.Tensor:
-    """(B,2,H,W) fp32 -> (B,C,H,W) bf16 channels_last: W x + b, then LeakyReLU(0.2) or a mask multiply."""
+def rgb_expand(x: th.Tensor, w: th.Tensor, b=None, mask_src=None, lrelu=False, out_dtype=th.bfloat16) -> th.Tensor:
+    """(B,2,H,W) fp32 -> (B,C,H,W) bf16 (or fp32) channels_last: W x + b, then LeakyReLU(0.2) or a mask multiply."""
     x = _planes(x, "rgb_expand x")
     B, _, H, W = x.shape
     C = w.shape[0]
     w = w.float().reshape(C, 2).contiguous()
-    y = th.empty((B, C, H, W), dtype=th.bfloat16, device=x.device, memory_format=th.channels_last)
+    if mask_src is not None:
+        out_dtype = mask_src.dtype
+    y = th.empty((B, C, H, W), dtype=out_dtype, device=x.device, memory_format=th.channels_last)
     mode = 1 if lrelu else (2 if mask_src is not None else 0)
     if mask_src is not None:
         _check_act(mask_src, "rgb_expand mask")
     with th.cuda.device(x.device):
-        _lib.check(_l().mg_rgb_expand_bf16(x.data_ptr(), w.data_ptr(), b.float().contiguous().data_ptr() if b is not None else None,
+        _lib.check(getattr(_l(), "mg_rgb_expand" + _sfx(y))(x.data_ptr(), w.data_ptr(), b.float().contiguous().data_ptr() if b is not None else None,
                                            mask_src.data_ptr() if mask_src is not None else None, y.data_ptr(),
                                            B, H * W, C, mode, _stream()), "mg_rgb_expand_bf16")
     return y
@@ -223,9 +283,9 @@ def rgb_project(a: th.Tensor, w: th.Tensor, bias=None, mask_src=None, tanh=False
     rs, cs = (1, 2) if w_is_c_by_2 else (C, 1)
     out = th.empty((B, 2, H, W), dtype=th.float32, device=a.device)
     if mask_src is not None:
-        _check_act(mask_src, "rgb_project mask")
+        _check_act(mask_src, "rgb_project mask", a.dtype)
     with th.cuda.device(a.device):
-        _lib.check(_l().mg_rgb_project_bf16(a.data_ptr(), w.data_ptr(), rs, cs, bias.float().contiguous().data_ptr() if bias is not None else None,
+        _lib.check(getattr(_l(), "mg_rgb_project" + _sfx(a))(a.data_ptr(), w.data_ptr(), rs, cs, bias.float().contiguous().data_ptr() if bias is not None else None,
                                             mask_src.data_ptr() if mask_src is not None else None, out.data_ptr(),
                                             B, H * W, C, 1 if tanh else 0, _stream()), "mg_rgb_project_bf16")
     return out
@@ -239,9 +299,9 @@ def rgb_wgrad(g: th.Tensor, mask_src, x: th.Tensor):
     gw = th.zeros((C, 2), dtype=th.float32, device=g.device)
     gb = th.zeros((C,), dtype=th.float32, device=g.device)
     if mask_src is not None:
-        _check_act(mask_src, "rgb_wgrad mask")
+        _check_act(mask_src, "rgb_wgrad mask", g.dtype)
     with th.cuda.device(g.device):
-        _lib.check(_l().mg_rgb_wgrad_bf16(g.data_ptr(), mask_src.data_ptr() if mask_src is not None else None, x.data_ptr(),
+        _lib.check(getattr(_l(), "mg_rgb_wgrad" + _sfx(g))(g.data_ptr(), mask_src.data_ptr() if mask_src is not None else None, x.data_ptr(),
                                           gw.data_ptr(), gb.data_ptr(), B, H * W, C, _stream()), "mg_rgb_wgrad_bf16")
     return gw, gb
 
@@ -253,21 +313,21 @@ def pool2(x: th.Tensor, adjoint: bool = False, sum_pool: bool = False) -> th.Ten
     B, C, H, W = x.shape
     if adjoint:
         ho, wo = H, W
-        out = th.empty((B, C, 2 * H, 2 * W), dtype=th.bfloat16, device=x.device, memory_format=th.channels_last)
+        out = th.empty((B, C, 2 * H, 2 * W), dtype=x.dtype, device=x.device, memory_format=th.channels_last)
     else:
         assert H % 2 == 0 and W % 2 == 0
         ho, wo = H // 2, W // 2
-        out = th.empty((B, C, ho, wo), dtype=th.bfloat16, device=x.device, memory_format=th.channels_last)
+        out = th.empty((B, C, ho, wo), dtype=x.dtype, device=x.device, memory_format=th.channels_last)
     with th.cuda.device(x.device):
-        _lib.check(_l().mg_pool2_bf16(x.data_ptr(), out.data_ptr(), B, ho, wo, C, 1 if adjoint else (2 if sum_pool else 0), _stream()),
+        _lib.check(getattr(_l(), "mg_pool2" + _sfx(x))(x.data_ptr(), out.data_ptr(), B, ho, wo, C, 1 if adjoint else (2 if sum_pool else 0), _stream()),
                    "mg_pool2_bf16")
     return out
 
 
 def pixelnorm_lrelu_bwd(go: th.Tensor, o: th.Tensor, inv: th.Tensor, want_bias_grad: bool = True):
     """Backward of LeakyReLU -> PixelNorm (saved normalised output `o`, saved 1/norm `inv`): (gz bf16, gb fp32)."""
-    go = as_act(go)
     _check_act(o, "pixelnorm_lrelu_bwd o")
+    go = as_act(go, o.dtype)
     B, C, H, W = o.shape
     inv = inv.float().contiguous()
     gz = th.empty_like(o)
@@ -275,7 +335,7 @@ def pixelnorm_lrelu_bwd(go: th.Tensor, o: th.Tensor, inv: th.Tensor, want_bias_g
     l = _l()
     ws = _workspace(o.device, l.mg_colsum_workspace_bytes(C), "colsum") if want_bias_grad else None
     with th.cuda.device(o.device):
-        _lib.check(l.mg_pixelnorm_lrelu_bwd_bf16(go.data_ptr(), o.data_ptr(), inv.data_ptr(), gz.data_ptr(),
+        _lib.check(getattr(l, "mg_pixelnorm_lrelu_bwd" + _sfx(o))(go.data_ptr(), o.data_ptr(), inv.data_ptr(), gz.data_ptr(),
                                                  gb.data_ptr() if gb is not None else None,
                                                  ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
                                                  B * H * W, C, _stream()),
@@ -285,15 +345,15 @@ def pixelnorm_lrelu_bwd(go: th.Tensor, o: th.Tensor, inv: th.Tensor, want_bias_g
 
 def lrelu_bwd(gy: th.Tensor, y: th.Tensor, want_bias_grad: bool = True):
     """gz = gy * (y > 0 ? 1 : 0.2) and, fused, the bias gradient sum over pixels (fp32)."""
-    gy = as_act(gy)
     _check_act(y, "lrelu_bwd y")
+    gy = as_act(gy, y.dtype)
     B, C, H, W = y.shape
     gz = th.empty_like(y)
     gb = th.empty((C,), dtype=th.float32, device=y.device) if want_bias_grad else None      # overwritten by the kernel
     l = _l()
     ws = _workspace(y.device, l.mg_colsum_workspace_bytes(C), "colsum") if want_bias_grad else None
     with th.cuda.device(y.device):
-        _lib.check(l.mg_lrelu_bwd_bf16(gy.data_ptr(), y.data_ptr(), gz.data_ptr(), gb.data_ptr() if gb is not None else None,
+        _lib.check(getattr(l, "mg_lrelu_bwd" + _sfx(y))(gy.data_ptr(), y.data_ptr(), gz.data_ptr(), gb.data_ptr() if gb is not None else None,
                                        ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
                                        B * H * W, C, _stream()), "mg_lrelu_bwd_bf16")
     return gz, gb
@@ -302,8 +362,8 @@ def lrelu_bwd(gy: th.Tensor, y: th.Tensor, want_bias_grad: bool = True):
 def unpool_lrelu_bwd(gp: th.Tensor, h: th.Tensor, want_bias_grad: bool = True):
     """Backward of LeakyReLU -> AvgPool2d(2,2) in one pass: gz = 0.25 * up2(gp) * (h > 0 ? 1 : 0.2) at the resolution of
     `h`, and the bias gradient sum over pixels (fp32)."""
-    gp = as_act(gp)
     _check_act(h, "unpool_lrelu_bwd h")
+    gp = as_act(gp, h.dtype)
     B, C, H, W = h.shape
     assert gp.shape == (B, C, H // 2, W // 2) and H % 2 == 0 and W % 2 == 0, (gp.shape, h.shape)
     gz = th.empty_like(h)
@@ -311,7 +371,7 @@ def unpool_lrelu_bwd(gp: th.Tensor, h: th.Tensor, want_bias_grad: bool = True):
     l = _l()
     ws = _workspace(h.device, l.mg_colsum_workspace_bytes(C), "colsum") if want_bias_grad else None
     with th.cuda.device(h.device):
-        _lib.check(l.mg_unpool2_lrelu_bwd_bf16(gp.data_ptr(), h.data_ptr(), gz.data_ptr(), gb.data_ptr() if gb is not None else None,
+        _lib.check(getattr(l, "mg_unpool2_lrelu_bwd" + _sfx(h))(gp.data_ptr(), h.data_ptr(), gz.data_ptr(), gb.data_ptr() if gb is not None else None,
                                                ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
                                                B, H // 2, W // 2, C, _stream()), "mg_unpool2_lrelu_bwd_bf16")
     return gz, gb

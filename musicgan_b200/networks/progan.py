@@ -58,8 +58,8 @@ class Block(nn.Sequential):
             _conv3(in_channels, out_channels), nn.LeakyReLU(2e-1), PixelNorm())
 
     def forward(self, x: th.Tensor) -> th.Tensor:
-        h = fn.GenConv.apply(x, self[0].weight, self[0].bias, False)
-        return fn.GenConv.apply(h, self[4].weight, self[4].bias, True)
+        h = fn.GenConv.apply(fn.prep(x, x.shape[2]), self[0].weight, self[0].bias, False)
+        return fn.GenConv.apply(fn.prep(h, 2 * h.shape[2]), self[4].weight, self[4].bias, True)
 
 
 class ToMagnPhaseLayer(nn.Sequential):
@@ -69,7 +69,7 @@ class ToMagnPhaseLayer(nn.Sequential):
         super().__init__(nn.Conv2d(in_channels, 2, kernel_size=(1, 1), stride=(1, 1)), nn.Tanh())
 
     def forward(self, x: th.Tensor) -> th.Tensor:
-        return fn.ToRgbTanh.apply(x, self[0].weight, self[0].bias)
+        return fn.ToRgbTanh.apply(fn.prep(x, x.shape[2]), self[0].weight, self[0].bias)
 
 
 class _UpsampledToMagnPhase(nn.Sequential):
@@ -97,7 +97,7 @@ class Generator(nn.Module):
 
     def forward(self, z: th.Tensor, alpha: float) -> th.Tensor:
         _require_cuda(z, "Generator.forward")
-        out = fn.ops.as_act(z)
+        out = z
         for i in range(self.curr_layer):
             out = self.__gen_blocks[i](out)
         top = self.__gen_blocks[self.curr_layer](out)
@@ -145,8 +145,8 @@ class ConvBlock(nn.Sequential):
                          _conv3(out_channels, out_channels), nn.LeakyReLU(2e-1))
 
     def forward(self, x: th.Tensor) -> th.Tensor:
-        h = fn.ConvBiasLReLUPool.apply(x, self[0].weight, self[0].bias)      # conv + LReLU, pool; fused backward
-        return fn.ConvBiasLReLU.apply(h, self[3].weight, self[3].bias)
+        h = fn.ConvBiasLReLUPool.apply(fn.prep(x, x.shape[2]), self[0].weight, self[0].bias)      # conv + LReLU, pool; fused backward
+        return fn.ConvBiasLReLU.apply(fn.prep(h, h.shape[2]), self[3].weight, self[3].bias)
 
 
 class MagPhaseLayer(nn.Sequential):
@@ -156,7 +156,8 @@ class MagPhaseLayer(nn.Sequential):
         super().__init__(nn.Conv2d(2, out_channels, kernel_size=(1, 1), stride=(1, 1)), nn.LeakyReLU(2e-1))
 
     def forward(self, x: th.Tensor) -> th.Tensor:
-        return fn.RgbExpand.apply(x, self[0].weight, self[0].bias, None, True)
+        return fn.RgbExpand.apply(x, self[0].weight, self[0].bias, None, True,
+                                  th.float32 if fn.ops.is_precise(x.shape[2]) else th.bfloat16)
 
 
 class _PooledMagPhase(nn.Sequential):
@@ -183,7 +184,8 @@ class Discriminator(nn.Module):
         _require_cuda(x, "Discriminator.forward")
         out = self.__conv_blocks[self.__curr_layer](self.__start_block(x))
         if self.__last_start_block is not None:
-            out = th.lerp(self.__last_start_block(x), out, alpha)       # alpha * out + (1 - alpha) * old, one kernel, one rounding
+            old = self.__last_start_block(x)
+            out = th.lerp(old, out.to(old.dtype), alpha)       # alpha * out + (1 - alpha) * old, one kernel, one rounding
         for i in range(self.__curr_layer + 1, len(self.__conv_blocks)):
             out = self.__conv_blocks[i](out)
         return self.__clf(out.flatten(1, -1).float())

@@ -162,13 +162,15 @@ class Saver:
 
     @property
     def curr_save(self) -> int:
-        return self._curr_save
+        return self._curr_save - 1          # utils.py:236-239: the last SAVED index
 
     @property
     def save_counter(self) -> int:
-        return self._counter
+        return self._counter % self._every  # utils.py:241-242
 
     def request_save(self, gen, disc, optim_gen, optim_disc, alpha: float) -> bool:
+        # utils.py:209-233: count first, save when the count is a multiple of save_every (first files at call #save_every)
+        self._counter += 1
         if self._counter % self._every == 0:
             k = self._curr_save
             th.save(disc.state_dict(), join(self._dir, f"disc_{k}.pt"))
@@ -176,7 +178,5 @@ class Saver:
             th.save(gen.state_dict(), join(self._dir, f"gen_{k}.pt"))
             th.save(optim_gen.state_dict(), join(self._dir, f"optim_gen_{k}.pt"))
             self._curr_save += 1
-            self._counter += 1
             return True
-        self._counter += 1
         return False

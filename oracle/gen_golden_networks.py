@@ -8,16 +8,24 @@ import torch as th
 
 from oracle import networks_oracle as no
 
-CASES = {   # name -> (stage, batch, alpha)
+CASES = {   # name -> (stage, batch, alpha): every stage of the progressive schedule (train.py:258-272) + the benchmarked shape
     "stage0_b2": (0, 2, 1.0),
+    "stage1_b2": (1, 2, 0.5),
     "stage2_b3": (2, 3, 0.5),
+    "stage3_b2": (3, 2, 0.75),
     "stage4_b2": (4, 2, 0.25),
+    "stage5_b2": (5, 2, 0.5),
+    "stage6_b1": (6, 1, 1.0),
+    "stage7_b1": (7, 1, 0.5),
+    "stage7_b8": (7, 8, 0.5),          # BASELINE config 2: 512 x 512, batch 8
 }
+SMALL_CASES = [k for k, v in CASES.items() if v[0] <= 4]      # the CPU suite re-checks the oracle on these only (seconds)
+MAX_STORED = 1 << 16                                          # elements of x_fake kept in a fixture (strided subsample)
 
 
 def case_inputs(name):
     stage, batch, alpha = CASES[name]
-    g = th.Generator().manual_seed(1000 + stage)
+    g = th.Generator().manual_seed(1000 + stage + (100 * batch if name == "stage7_b8" else 0))
     r = 4 * 2 ** stage
     z = th.randn(batch, 32, 2, 2, generator=g)
     z2 = th.randn(batch, 32, 2, 2, generator=g)
@@ -72,15 +80,31 @@ def main(ref_networks, gold_dir):
         o_g = no.g_step(sd_g, sd_d, z2, alpha, stage)
         ex = th.equal(o_d["x_fake"], x_fake.detach()) and th.equal(o_d["out_real"], out_real.detach()) and th.equal(o_g["out_fake"], out_fake2.detach())
         rel = lambda a, b: ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
-        worst_d = max(rel(o_d["grads"][k], d_grads[k]) for k in d_grads)
+        # The critic gradient is g_fake - g_real + g_gp with g_real ~ g_fake (random-init critic): it cancels to 1e-3 ...
+        # 1e-7 of its terms, and at that level even the reference's own fp32 summation order shows (detached vs attached
+        # fake batch: 1e-3 relative at stage 6).  Oracle and reference are therefore compared on the scale of the terms,
+        # and the conditioning number is stored with the fixture.
+        def term(fn):
+            d = no._leaf(sd_d)
+            fn(d).backward()
+            return th.cat([v.grad.flatten() for v in d.values() if v.grad is not None]).double().norm().item()
+        xf = x_fake.detach()
+        terms = (term(lambda d: no.disc_forward(d, x_real, alpha, stage).mean()) + term(lambda d: no.disc_forward(d, xf, alpha, stage).mean())
+                 + term(lambda d: no.gradient_penalty(d, x_real, xf, alpha, stage, eps)))
+        cat = lambda G, keys: th.cat([G[k].flatten() for k in keys]).double()
+        kd = list(d_grads)
+        total = cat(d_grads, kd).norm().item()
+        worst_d = (cat(o_d["grads"], kd) - cat(d_grads, kd)).norm().item() / terms
         worst_g = max(rel(o_g["grads"][k], g_grads[k]) for k in g_grads)
-        print(f"networks/{name}: forward bit-exact {ex}; oracle-vs-reference grad rel-L2 worst D {worst_d:.2e} G {worst_g:.2e}; "
+        print(f"networks/{name}: forward bit-exact {ex}; oracle-vs-reference: D grads {worst_d:.2e} of the term scale "
+              f"(|terms| / |total| = {terms / total:.1e}), G grads worst rel-L2 {worst_g:.2e}; "
               f"gp {gp.item():.6f} vs {o_d['gp'].item():.6f}; params without grad: D {len(none_d)} G {len(none_g)}")
-        assert worst_d < 1e-4 and worst_g < 1e-4
+        assert worst_d < 1e-6 and worst_g < 1e-4
 
+        xf_stride = max(1, -(-x_fake.numel() // MAX_STORED))
         arrays = dict(stage=np.int64(stage), batch=np.int64(batch), alpha=np.float64(alpha),
-                      forward_bit_exact=np.bool_(ex),
-                      x_fake=x_fake.detach().numpy(), out_real=out_real.detach().numpy(), out_fake=out_fake.detach().numpy(),
+                      forward_bit_exact=np.bool_(ex), critic_cond=np.float64(terms / total), x_fake_stride=np.int64(xf_stride),
+                      x_fake=x_fake.detach().contiguous().view(-1)[::xf_stride].numpy().copy(), out_real=out_real.detach().numpy(), out_fake=out_fake.detach().numpy(),
                       d_loss=np.float64(d_loss.item()), gp=np.float64(gp.item()), g_loss=np.float64(g_loss.item()),
                       out_fake2=out_fake2.detach().numpy(),
                       none_d=np.array(none_d), none_g=np.array(none_g))

@@ -94,7 +94,7 @@ def test_fused_epilogue_and_upsample(B, Cin, Cout, H, W):
     g = torch.Generator().manual_seed(6)
     w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).cuda()
     b = torch.randn(Cout, generator=g).cuda()
-    fits = 9 * Cin * Cout * 2 <= 120 * 1024
+    fits = 9 * Cin * Cout * 2 <= 184 * 1024
     if not fits:
         y = ops.conv3x3(x, w, b, lrelu=True, upsample_in=True)
         ref = F.leaky_relu(F.conv2d(F.interpolate(x.float(), scale_factor=2.0, mode="nearest"), w.bfloat16().float(), b, padding=1), 0.2)
@@ -231,3 +231,123 @@ def test_pool2_planes_matches_torch_bitwise():
     gs2 = gsmall.clone().requires_grad_(True)
     gg = torch.autograd.grad(fn.UnpoolPlanes.apply(gs2), gs2, x)[0]
     assert torch.equal(gg, F.avg_pool2d(x, 2, 2))
+
+
+# ---- precise path: fp32 activations, split-bf16 operands (conv_split.cu) ---------------------------------------------
+def _mk32(B, C, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, C, H, W, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+
+
+SPLIT_SHAPES = [  # (B, Cin, Cout, H, W): the layers with output height <= 32 of both networks + ragged sizes
+    (2, 32, 32, 2, 2), (2, 32, 128, 4, 4), (3, 128, 112, 8, 8), (2, 112, 96, 16, 16), (2, 96, 80, 32, 32),
+    (2, 80, 96, 32, 32), (4, 144, 160, 2, 2), (5, 160, 160, 1, 1), (1, 16, 16, 20, 12), (1, 48, 64, 32, 72),
+]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", SPLIT_SHAPES)
+def test_split_fprop_and_dgrad(B, Cin, Cout, H, W):
+    """x = hi + lo, w = hi + lo, three MMAs per K step: the result must sit within a few 2^-17 of the fp64 convolution
+    of the fp32 operands (a bf16-operand kernel is at 2^-9)."""
+    from musicgan_b200.networks import ops
+    torch.backends.cudnn.allow_tf32 = False
+    x = _mk32(B, Cin, H, W, 51)
+    g = torch.Generator().manual_seed(52)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    y = ops.conv3x3(x, w, b, lrelu=True)
+    assert y.dtype == torch.float32 and y.is_contiguous(memory_format=torch.channels_last)
+    ref = F.leaky_relu(F.conv2d(x.double(), w.double(), b.double(), padding=1), 0.2)
+    e = ((y.double() - ref).norm() / ref.norm()).item()
+    assert e <= 2e-5, e
+    dy = _mk32(B, Cout, H, W, 53)
+    dx = ops.conv3x3(dy, w, None, dgrad=True)
+    ref = F.conv_transpose2d(dy.double(), w.double(), padding=1)
+    e = ((dx.double() - ref).norm() / ref.norm()).item()
+    assert dx.shape == (B, Cin, H, W) and e <= 2e-5, e
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 32, 128, 4, 4), (2, 128, 112, 8, 8), (1, 96, 80, 32, 32), (2, 32, 16, 24, 40)])
+def test_split_fused_epilogue_and_upsample(B, Cin, Cout, H, W):
+    from musicgan_b200.networks import ops
+    x = _mk32(B, Cin, H // 2, W // 2, 55)
+    g = torch.Generator().manual_seed(56)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    y, inv = ops.conv3x3(x, w, b, lrelu=True, pixelnorm=True, upsample_in=True, want_inv_norm=True)
+    z = F.leaky_relu(F.conv2d(F.interpolate(x.double(), scale_factor=2.0, mode="nearest"), w.double(), b.double(), padding=1), 0.2)
+    ref = z / torch.sqrt(z.pow(2.0).mean(dim=1, keepdim=True) + 1e-8)
+    e = ((y.double() - ref).norm() / ref.norm()).item()
+    assert e <= 2e-5, e
+    ref_inv = 1.0 / torch.sqrt(z.pow(2.0).mean(dim=1) + 1e-8)
+    assert ((inv.double() - ref_inv).norm() / ref_inv.norm()).item() <= 2e-5
+
+
+def test_split_weights_in_the_bf16_kernel():
+    """flag 16: weights enter as hi + lo bf16 pairs.  A centre-tap weight of 256.5 (hi = 256, lo = 0.5) on a
+    channel-diagonal convolution must give bf16(256.5 * x), not bf16(256 * x)."""
+    from musicgan_b200.networks import ops
+    for C in (16, 48, 80):
+        x = _mk(2, C, 32, 24, 61)
+        w = torch.zeros(C, C, 3, 3, device="cuda")
+        w[torch.arange(C), torch.arange(C), 1, 1] = 256.5
+        y = ops.conv3x3(x, w, None, split_w=True).float()
+        want = (256.5 * x.float()).bfloat16().float()
+        plain = (256.0 * x.float()).bfloat16().float()
+        assert (y == want).float().mean().item() >= 0.999
+        assert (want != plain).float().mean().item() >= 0.2        # the test can tell the two apart
+        y1 = ops.conv3x3(x, w, None).float()                       # without the flag: bf16(w) = 256
+        assert (y1 == plain).float().mean().item() >= 0.999
+    # and through the PixelNorm epilogue of the widest such layer (all Cout in one slice, weights 2 x 92 KB)
+    x = _mk(1, 80, 32, 32, 62)
+    g = torch.Generator().manual_seed(63)
+    w = (torch.randn(64, 80, 3, 3, generator=g) / (3 * 80 ** 0.5)).cuda()
+    b = torch.randn(64, generator=g).cuda()
+    y = ops.conv3x3(x, w, b, lrelu=True, pixelnorm=True, upsample_in=True, split_w=True)
+    z = F.leaky_relu(F.conv2d(F.interpolate(x.float(), scale_factor=2.0, mode="nearest"), w, b, padding=1), 0.2)
+    ref = z / torch.sqrt(z.pow(2.0).mean(dim=1, keepdim=True) + 1e-8)
+    assert rel_l2(y, ref) <= 4e-3, rel_l2(y, ref)
+
+
+def test_pointwise_kernels_on_fp32_activations():
+    """The fp32-activation instantiations of the memory-bound kernels against torch fp32."""
+    from musicgan_b200.networks import ops
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(71)
+    B, C, H, W = 3, 48, 12, 20
+    a, m, gy = _mk32(B, C, H, W, 72), _mk32(B, C, H, W, 73), _mk32(B, C, H, W, 74)
+    mask = torch.where(m > 0, 1.0, 0.2)
+    gz, gb = ops.lrelu_bwd(gy, m)
+    assert gz.dtype == torch.float32 and torch.equal(gz, gy * mask)
+    assert torch.allclose(gb, (gy * mask).sum((0, 2, 3)), rtol=1e-5, atol=1e-4)
+    gp = _mk32(B, C, H // 2, W // 2, 75)
+    gz2, gb2 = ops.unpool_lrelu_bwd(gp, m)
+    ref = 0.25 * F.interpolate(gp, scale_factor=2.0, mode="nearest") * mask
+    assert torch.equal(gz2, ref) and torch.allclose(gb2, ref.sum((0, 2, 3)), rtol=1e-5, atol=1e-4)
+    assert torch.allclose(ops.pool2(a), F.avg_pool2d(a, 2, 2), rtol=1e-6, atol=1e-6)
+    assert torch.equal(ops.pool2(gp, adjoint=True), F.interpolate(gp, scale_factor=2.0, mode="nearest") * 0.25)
+    assert torch.allclose(ops.pool2(a, sum_pool=True), F.avg_pool2d(a, 2, 2) * 4, rtol=1e-6, atol=1e-6)
+    x = (torch.rand(B, 2, H, W, generator=g) * 2 - 1).cuda()
+    w = torch.randn(C, 2, 1, 1, generator=g).cuda()
+    b = torch.randn(C, generator=g).cuda()
+    y = ops.rgb_expand(x, w, b, lrelu=True, out_dtype=torch.float32)
+    assert y.dtype == torch.float32 and rel_l2(y, F.leaky_relu(F.conv2d(x, w, b), 0.2)) <= 1e-6
+    assert rel_l2(ops.rgb_expand(x, w, None, mask_src=m), F.conv2d(x, w) * mask) <= 1e-6
+    w2 = torch.randn(2, C, 1, 1, generator=g).cuda()
+    b2 = torch.randn(2, generator=g).cuda()
+    assert rel_l2(ops.rgb_project(a, w2, bias=b2, tanh=True), torch.tanh(F.conv2d(a, w2, b2))) <= 1e-5
+    assert rel_l2(ops.rgb_project(a, w, mask_src=m, w_is_c_by_2=True), F.conv_transpose2d(a * mask, w)) <= 1e-5
+    gw, gbb = ops.rgb_wgrad(a, m, x)
+    assert rel_l2(gw, torch.einsum("bchw,bkhw->ck", a * mask, x)) <= 1e-4 and rel_l2(gbb, (a * mask).sum((0, 2, 3))) <= 1e-4
+    # PixelNorm + LeakyReLU backward against autograd on fp32
+    z = _mk32(B, C, H, W, 76).requires_grad_(True)
+    t = F.leaky_relu(z, 0.2)
+    n = torch.sqrt(t.pow(2.0).mean(dim=1, keepdim=True) + 1e-8)
+    o = t / n
+    gz3, gb3 = ops.pixelnorm_lrelu_bwd(gy, o.detach().contiguous(memory_format=torch.channels_last), (1.0 / n.detach())[:, 0].contiguous())
+    (auto,) = torch.autograd.grad(o, z, gy)
+    assert rel_l2(gz3, auto) <= 1e-5 and rel_l2(gb3, auto.sum((0, 2, 3))) <= 1e-4
+    # weight gradient from fp32 activations (bf16 operands inside: terminal product)
+    dw = ops.conv3x3_wgrad(gy, a)
+    ref = torch.nn.grad.conv2d_weight(a.bfloat16().float(), (C, C, 3, 3), gy.bfloat16().float(), padding=1)
+    assert rel_l2(dw, ref) <= 1e-4

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import networks_oracle as no
-from oracle.gen_golden_networks import CASES, case_inputs
+from oracle.gen_golden_networks import CASES, SMALL_CASES, case_inputs
 
 
 @pytest.mark.parametrize("stage", [0, 1, 4, 7])
@@ -38,13 +38,13 @@ def test_cpu_forward_fails_loudly():
         networks.Generator(8)
 
 
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", SMALL_CASES)
 def test_oracle_matches_reference_golden(golden_dir, name):
     gold = np.load(os.path.join(golden_dir, f"networks_{name}.npz"))
     stage, batch, alpha, z, z2, x_real, eps = case_inputs(name)
     sd_g, sd_d = no.make_state("gen", stage, 11), no.make_state("disc", stage, 12)
     d = no.d_step(sd_g, sd_d, z, x_real, eps, alpha, stage)
-    np.testing.assert_allclose(d["x_fake"].numpy(), gold["x_fake"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(d["x_fake"].contiguous().view(-1)[::int(gold["x_fake_stride"])].numpy(), gold["x_fake"], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(d["out_real"].numpy(), gold["out_real"], rtol=1e-4, atol=1e-6)
     assert abs(d["gp"].item() - float(gold["gp"])) <= 1e-5 * abs(float(gold["gp"]))
     for k, v in d["grads"].items():

@@ -38,7 +38,11 @@ def cat_grads(named, ref):
     return torch.cat([named[k].detach().float().cpu().flatten() for k in keys]), torch.cat([ref[k].flatten() for k in keys])
 
 
-@pytest.mark.parametrize("name", list(CASES))
+BIG = {"stage7_b8"}                          # oracle takes tens of seconds on the host cores: run in the dedicated test
+STEP_CASES = [k for k in CASES if k not in BIG]
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
 def test_forward_vs_oracle(name):
     stage, batch, alpha, z, z2, x_real, eps = case_inputs(name)
     sd_g, sd_d = no.make_state("gen", stage, 11), no.make_state("disc", stage, 12)
@@ -47,11 +51,14 @@ def test_forward_vs_oracle(name):
         xf = gen(z.cuda(), alpha)
         ref_xf = no.gen_forward(sd_g, z, alpha, stage)
         assert xf.shape == ref_xf.shape and xf.dtype == torch.float32
-        assert rel(xf, ref_xf) <= TOL, rel(xf, ref_xf)
+        e_g = rel(xf, ref_xf)
         out = disc(x_real.cuda(), alpha)
         ref_out = no.disc_forward(sd_d, x_real, alpha, stage)
         assert out.shape == ref_out.shape == (batch, 1)
-        assert rel(out, ref_out) <= TOL, rel(out, ref_out)
+        e_d = rel(out, ref_out)
+        print(f"{name}: G output rel-L2 {e_g:.2e}; D output rel-L2 {e_d:.2e}")
+        assert e_g <= TOL, e_g
+        assert e_d <= TOL, e_d
 
 
 def _param_grads(module):
@@ -64,10 +71,20 @@ def _oracle_term_grads(sd_d, fn_of_leaf):
     return {k: v.grad for k, v in d.items()}
 
 
-@pytest.mark.parametrize("name", list(CASES))
+def _norm(grads):
+    return torch.cat([v.flatten() for v in grads.values() if v is not None]).double().norm().item()
+
+
+def _our_term(disc, fn_of_disc):
+    disc.zero_grad()
+    fn_of_disc(disc).backward()
+    return _param_grads(disc)
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
 def test_discriminator_first_order_gradients(name):
-    """Gradients of mean(D(x)) w.r.t. every active D parameter (the well-conditioned building block of the
-    critic loss, train.py:155-159): rel-L2 <= 1e-2 against the fp32 oracle."""
+    """Gradients of mean(D(x)) w.r.t. every active D parameter (the building block of the critic loss,
+    train.py:155-159): rel-L2 <= 1e-2 against the fp32 oracle."""
     stage, batch, alpha, z, z2, x_real, eps = case_inputs(name)
     sd_g, sd_d = no.make_state("gen", stage, 11), no.make_state("disc", stage, 12)
     _, disc = build(stage, sd_g, sd_d)
@@ -80,44 +97,51 @@ def test_discriminator_first_order_gradients(name):
     assert e <= TOL, e
 
 
-@pytest.mark.parametrize("name", list(CASES))
-def test_critic_and_generator_step_gradients(golden_dir, name):
-    """One critic step and one generator step (train.py:143-214) against the oracle and the reference goldens.
-    The critic gradient is a DIFFERENCE of two nearly equal terms (real minus fake) plus the penalty term, so its
-    error is measured against the summed norms of the three terms (each term is checked on its own elsewhere)."""
+def _check_steps(name, golden_dir):
+    """One critic step and one generator step (train.py:143-214) against the fp32 oracle and the reference goldens; plain
+    relative L2 <= 1e-2, no floor, for: the generator-step gradient, and each of the three terms of the critic gradient
+    (mean D(real), mean D(fake), gradient penalty).  The critic-step TOTAL  g_fake - g_real + g_gp  is printed with its
+    conditioning |terms| / |total| (15 at stage 0 ... 5e6 at stage 7, stored in the fixtures: with a random-init critic
+    g_real ~ g_fake, and at 1e-6 of the terms the reference's own fp32 summation order shows); its error is asserted on
+    the scale it is computed at, 1e-2 * (|g_real| + |g_fake| + |g_gp|), which the three term bounds imply."""
     from musicgan_b200 import train_step
     stage, batch, alpha, z, z2, x_real, eps = case_inputs(name)
     sd_g, sd_d = no.make_state("gen", stage, 11), no.make_state("disc", stage, 12)
     gen, disc = build(stage, sd_g, sd_d)
     gold = np.load(os.path.join(golden_dir, f"networks_{name}.npz"))
+    xr, ec = x_real.cuda(), eps.cuda()
 
-    d_loss, gp, out_real, out_fake = train_step.critic_step(gen, disc, None, z.cuda(), x_real.cuda(), alpha, eps=eps.cuda(), step=False)
+    d_loss, gp, out_real, out_fake = train_step.critic_step(gen, disc, None, z.cuda(), xr, alpha, eps=ec, step=False)
     ref = no.d_step(sd_g, sd_d, z, x_real, eps, alpha, stage)
     named = dict(disc.named_parameters())
     got_none = sorted(k for k, p in named.items() if p.grad is None)
     assert got_none == sorted(k for k, v in ref["grads"].items() if v is None) == sorted(gold["none_d"].tolist())
-    g, r = cat_grads(_param_grads(disc), ref["grads"])
-    x_fake = ref["x_fake"]
-    t_real = _oracle_term_grads(sd_d, lambda d: no.disc_forward(d, x_real, alpha, stage).mean())
-    t_fake = _oracle_term_grads(sd_d, lambda d: no.disc_forward(d, x_fake, alpha, stage).mean())
-    t_gp = _oracle_term_grads(sd_d, lambda d: no.gradient_penalty(d, x_real, x_fake, alpha, stage, eps))
-    denom = sum(torch.cat([v.flatten() for v in t.values() if v is not None]).double().norm().item() for t in (t_real, t_fake, t_gp))
-    e_terms = (g.double() - r.double()).norm().item() / denom
-    # noise floor in the same normalisation: the fp32 oracle's own critic gradient when ONLY the weights of G and D are
-    # rounded to bf16 (the penalty term is ill conditioned, see test_gradient_penalty_double_backward)
-    rb = lambda sd: {k: v.bfloat16().float() for k, v in sd.items()}
-    refb = no.d_step(rb(sd_g), rb(sd_d), z, x_real, eps, alpha, stage)
-    keys = [k for k, v in ref["grads"].items() if v is not None]
-    floor = (torch.cat([refb["grads"][k].flatten() for k in keys]).double()
-             - torch.cat([ref["grads"][k].flatten() for k in keys]).double()).norm().item() / denom
-    print(f"{name}: critic-step grads: error / (|g_real|+|g_fake|+|g_gp|) = {e_terms:.2e} (oracle floor under bf16 weight "
-          f"rounding {floor:.2e}; plain rel-L2 of the difference {rel(g, r):.2e}); "
-          f"d_loss {d_loss.item():.6f} vs {ref['loss'].item():.6f}; gp {gp.item():.5f} vs {ref['gp'].item():.5f}")
-    assert e_terms <= max(TOL, 2.5 * floor), (e_terms, floor)        # same factor as the penalty term on its own
-    assert abs(gp.item() - float(gold["gp"])) <= 1e-2 * abs(float(gold["gp"]))
-    assert rel(out_real, torch.from_numpy(gold["out_real"])) <= TOL
+    g_tot, r_tot = cat_grads(_param_grads(disc), ref["grads"])
     for p in gen.parameters():
         assert p.grad is None                       # fake batch detached: G untouched by the critic step
+    x_fake = ref["x_fake"]
+    with torch.no_grad():
+        our_fake = gen(z.cuda(), alpha)
+    terms = {
+        "real": (lambda d: d(xr, alpha).mean(), lambda d: no.disc_forward(d, x_real, alpha, stage).mean()),
+        "fake": (lambda d: d(our_fake, alpha).mean(), lambda d: no.disc_forward(d, x_fake, alpha, stage).mean()),
+        "gp": (lambda d: d.gradient_penalty(xr, our_fake, alpha, eps=ec), lambda d: no.gradient_penalty(d, x_real, x_fake, alpha, stage, eps)),
+    }
+    denom, errs = 0.0, {}
+    for key, (ours, oracle) in terms.items():
+        t_ref = _oracle_term_grads(sd_d, oracle)
+        g, r = cat_grads(_our_term(disc, ours), t_ref)
+        errs[key] = rel(g, r)
+        denom += _norm(t_ref)
+    e_plain = rel(g_tot, r_tot)
+    e_terms = (g_tot.double() - r_tot.double()).norm().item() / denom
+    print(f"{name}: critic-step gradient terms rel-L2: real {errs['real']:.2e} fake {errs['fake']:.2e} gp {errs['gp']:.2e}; "
+          f"total: {e_terms:.2e} of the term scale, plain rel-L2 {e_plain:.2e} at conditioning {float(gold['critic_cond']):.1e}; "
+          f"d_loss {d_loss.item():.6f} vs {ref['loss'].item():.6f}; gp {gp.item():.5f} vs {ref['gp'].item():.5f}")
+    assert max(errs.values()) <= TOL, errs
+    assert e_terms <= TOL, e_terms
+    assert abs(gp.item() - float(gold["gp"])) <= 1e-2 * abs(float(gold["gp"]))
+    assert rel(out_real, torch.from_numpy(gold["out_real"])) <= TOL
 
     g_loss, out_fake2 = train_step.generator_step(gen, disc, None, z2.cuda(), alpha, step=False)
     refg = no.g_step(sd_g, sd_d, z2, alpha, stage)
@@ -125,40 +149,33 @@ def test_critic_and_generator_step_gradients(golden_dir, name):
     assert sorted(k for k, p in named.items() if p.grad is None) == sorted(gold["none_g"].tolist())
     g, r = cat_grads(_param_grads(gen), refg["grads"])
     e = rel(g, r)
-    # noise floor: the fp32 oracle's own G gradient when ONLY the weights of G and D are rounded to bf16
-    rb = lambda sd: {k: v.bfloat16().float() for k, v in sd.items()}
-    refb = no.g_step(rb(sd_g), rb(sd_d), z2, alpha, stage)
-    keys = [k for k, v in refg["grads"].items() if v is not None]
-    floor = rel(torch.cat([refb["grads"][k].flatten() for k in keys]), torch.cat([refg["grads"][k].flatten() for k in keys]))
-    print(f"{name}: G-step grads rel-L2 {e:.2e} (oracle floor under bf16 weight rounding {floor:.2e}); "
-          f"g_loss {g_loss.item():.5f} vs {refg['loss'].item():.5f}")
-    assert e <= max(TOL, 2.0 * floor), (e, floor)
-    assert abs(g_loss.item() - float(gold["g_loss"])) <= 1e-2 * max(abs(float(gold["g_loss"])), 1e-3)
     worst = 0.0
     for k, p in named.items():
         if p.grad is None:
             continue
         ref_norm = float(gold["ggrad_digest/" + k][2])
         worst = max(worst, abs(p.grad.double().norm().item() - ref_norm) / max(ref_norm, 1e-30))
-    print(f"{name}: worst per-tensor G grad norm deviation vs reference golden {worst:.2e}")
-    assert worst <= max(3e-2, 2.0 * floor)
+    print(f"{name}: G-step grads rel-L2 {e:.2e}; worst per-tensor norm deviation vs reference golden {worst:.2e}; "
+          f"g_loss {g_loss.item():.5f} vs {refg['loss'].item():.5f}")
+    assert e <= TOL, e
+    assert worst <= 3 * TOL, worst
+    assert abs(g_loss.item() - float(gold["g_loss"])) <= 1e-2 * max(abs(float(gold["g_loss"])), 1e-3)
 
 
-def _bf16_weight_floor(sd_d, term):
-    """How much the fp32 ORACLE's own gradient moves when only its weights are rounded to bf16 (all arithmetic
-    still fp32): the noise floor any bf16-operand implementation inherits (cf. SURVEY B.4 for the IF path)."""
-    a = _oracle_term_grads(sd_d, term)
-    sd_b = {k: v.bfloat16().float() for k, v in sd_d.items()}
-    b = _oracle_term_grads(sd_b, term)
-    keys = [k for k in a if a[k] is not None]
-    return rel(torch.cat([b[k].flatten() for k in keys]), torch.cat([a[k].flatten() for k in keys]))
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_critic_and_generator_step_gradients(golden_dir, name):
+    _check_steps(name, golden_dir)
 
 
-@pytest.mark.parametrize("stage,batch,scale", [(1, 2, 3.0), (3, 2, 3.0), (4, 2, 1.0)])
+def test_benchmarked_shape_stage7_batch8(golden_dir):
+    """BASELINE config 2 itself: 512 x 512, batch 8, both fade paths alive -- the step bench.py times."""
+    _check_steps("stage7_b8", golden_dir)
+
+
+@pytest.mark.parametrize("stage,batch,scale", [(1, 2, 3.0), (3, 2, 3.0), (4, 2, 1.0), (6, 1, 1.0)])
 def test_gradient_penalty_double_backward(stage, batch, scale):
     """The GP term alone: its parameter gradients exist only through the double-backward graph
-    (fprop <-> dgrad <-> wgrad closure).  The GP gradient of a piecewise-linear critic is ill conditioned: rounding
-    just the WEIGHTS of the fp32 oracle to bf16 moves it by several percent, so the bound is that measured floor."""
+    (fprop <-> dgrad <-> wgrad closure).  Plain rel-L2 <= 1e-2 against the fp32 oracle."""
     g = torch.Generator().manual_seed(77 + stage)
     r = 4 * 2 ** stage
     x_real = torch.rand(batch, 2, r, r, generator=g) * 2 - 1
@@ -174,41 +191,9 @@ def test_gradient_penalty_double_backward(stage, batch, scale):
     ref_gp = term(sd_d)
     gg, rr = cat_grads(_param_grads(disc), ref)
     e = rel(gg, rr)
-    floor = _bf16_weight_floor(sd_d, term)
-    print(f"stage {stage} x{scale}: gp {gp.item():.5f} vs {ref_gp.item():.5f}; GP-only grads rel-L2 {e:.2e}; "
-          f"oracle floor under bf16 weight rounding {floor:.2e}")
+    print(f"stage {stage} x{scale}: gp {gp.item():.5f} vs {ref_gp.item():.5f}; GP-only grads rel-L2 {e:.2e}")
     assert abs(gp.item() - ref_gp.item()) <= 1e-2 * abs(ref_gp.item())
-    assert e <= max(TOL, 2.5 * floor), (e, floor)
-
-
-def test_full_resolution_stage7():
-    """BASELINE config 2 geometry (512 x 512, both fade paths alive, alpha = 0.5) at batch 1: outputs and
-    first-order gradients against the fp32 CPU oracle."""
-    stage, alpha = 7, 0.5
-    sd_g, sd_d = no.make_state("gen", stage, 21), no.make_state("disc", stage, 22)
-    gen, disc = build(stage, sd_g, sd_d)
-    g = torch.Generator().manual_seed(5)
-    z = torch.randn(1, 32, 2, 2, generator=g)
-    x_real = torch.rand(1, 2, 512, 512, generator=g) * 2 - 1
-    with torch.no_grad():
-        xf = gen(z.cuda(), alpha)
-        ref_xf = no.gen_forward(sd_g, z, alpha, stage)
-    assert tuple(xf.shape) == (1, 2, 512, 512)
-    e_g = rel(xf, ref_xf)
-    disc.zero_grad()
-    out = disc(x_real.cuda(), alpha)
-    out.mean().backward()
-    d = no._leaf(sd_d)
-    ref_out = no.disc_forward(d, x_real, alpha, stage)
-    ref_out.mean().backward()
-    gg, rr = cat_grads(_param_grads(disc), {k: v.grad for k, v in d.items()})
-    # the critic output is clf_w . features + clf_b; measure its error against |clf_w| . |features| + |clf_b| (the
-    # scale of the terms being summed), not against the possibly cancelling sum
-    feat = no.disc_forward(sd_d, x_real, alpha, stage, return_features=True)
-    scale = (sd_d["_Discriminator__clf.0.weight"].abs() @ feat.abs().t()).max().item() + sd_d["_Discriminator__clf.0.bias"].abs().item()
-    e_o, e_d = (out.detach().cpu() - ref_out.detach()).abs().max().item() / scale, rel(gg, rr)
-    print(f"stage 7: G output rel-L2 {e_g:.2e}; D output error / term scale {e_o:.2e}; D first-order grads {e_d:.2e}")
-    assert e_g <= 1.2 * TOL and e_o <= TOL and e_d <= TOL
+    assert e <= TOL, e
 
 
 def test_growth_and_shapes():
