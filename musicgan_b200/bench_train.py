@@ -25,21 +25,6 @@ def _build(stage: int, seed: int, device):
     return gen.to(device), disc.to(device)
 
 
-def _allreduce_grads(module, world: int):
-    import torch.distributed as dist
-    grads = [p.grad for p in module.parameters() if p.grad is not None]
-    if not grads:
-        return
-    flat = th.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat)
-    flat.div_(world)
-    off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
-        off += n
-
-
 def run(args, rank, world, local, timed_region, ClockSampler, peaks):
     from . import _lib, train_step
     from .networks import ops
@@ -57,12 +42,13 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
     reals_dev = [x.to(dev) for x in reals_host]
     it = [0]
 
+    from . import parallel
+    bucket_d = parallel.FlatGradBucket(disc.parameters()) if world > 1 else None      # the object `train` uses
+    bucket_g = parallel.FlatGradBucket(gen.parameters()) if world > 1 else None
     graphed = None
     if use_graphs:
         from .graphed import GraphedSteps
-        graphed = GraphedSteps(gen, disc, opt_g, opt_d, batch, 32, res, alpha,
-                               grad_sync_d=(lambda: _allreduce_grads(disc, world)) if world > 1 else None,
-                               grad_sync_g=(lambda: _allreduce_grads(gen, world)) if world > 1 else None)
+        graphed = GraphedSteps(gen, disc, opt_g, opt_d, batch, 32, res, alpha, bucket_d=bucket_d, bucket_g=bucket_g)
 
     def graphed_iter(x_real):
         stats = graphed.critic_step(x_real)
@@ -85,7 +71,7 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
         gen.zero_grad(); disc.zero_grad()
         (d_loss + gp).backward()
         if world > 1:
-            _allreduce_grads(disc, world)
+            bucket_d.sync()
         opt_d.step()
         loss = d_loss.detach() + gp.detach()
         if it[0] % 5 == 0:
@@ -94,7 +80,7 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
             gen.zero_grad(); disc.zero_grad()
             g_loss.backward()
             if world > 1:
-                _allreduce_grads(gen, world)
+                bucket_g.sync()
             opt_g.step()
         it[0] += 1
         return loss

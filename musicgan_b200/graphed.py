@@ -6,8 +6,9 @@ ONCE each (after a warm-up on a side stream) and replayed; all launches of libmu
 stream, so they are captured like any ATen kernel.  Packed-weight caches are invalidated before capture so that the
 weight re-pack kernels are part of the graph (weights change between replays).
 
-`alpha` is baked into the graphs: re-capture when it changes (bench: constant; `train` uses the eager steps while
-alpha ramps and may switch to graphs once alpha == 1).
+The fade-in weight `alpha` is a graph INPUT (a 0-dim device tensor read by the two blend kernels): `set_alpha()` moves
+it between replays, so one capture serves a whole stage of the progressive schedule; `train` re-captures at every
+`next_layer()` (new modules, new resolution).
 """
 from __future__ import annotations
 
@@ -22,11 +23,16 @@ from .networks import ops
 
 class GraphedSteps:
     def __init__(self, gen, disc, optim_gen, optim_disc, batch: int, rand_channels: int, resolution: int, alpha: float,
-                 grad_sync_d=None, grad_sync_g=None, warmup: int = 3, static_noise: bool = False,
-                 two_streams: bool = None):
+                 bucket_d=None, bucket_g=None, warmup: int = 3, static_noise: bool = False,
+                 two_streams: bool = None, preserve_state: bool = False):
         self.gen, self.disc, self.og, self.od = gen, disc, optim_gen, optim_disc
-        self.batch, self.alpha = batch, alpha
-        self.sync_d, self.sync_g = grad_sync_d, grad_sync_g
+        self.batch = batch
+        self.alpha = th.full((), float(alpha), dtype=th.float32, device=next(gen.parameters()).device)
+        self._alpha_host = float(alpha)
+        # parallel.FlatGradBucket of each network (data-parallel runs): the freshly computed gradients are gathered into
+        # the bucket, averaged over the ranks by ONE all-reduce node of the graph, and the parameters' .grad become views
+        # of the bucket
+        self.bucket_d, self.bucket_g = bucket_d, bucket_g
         dev = next(gen.parameters()).device
         self.x_real = th.zeros(batch, 2, resolution, resolution, device=dev)
         self.z_shape = (batch, rand_channels, 2, 2)
@@ -47,7 +53,18 @@ class GraphedSteps:
             # the parameters' AccumulateGrad nodes were created on another stream; gradients are collected by
             # autograd.grad (never accumulated), so the mismatch the engine warns about is intended
             th.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        # preserve_state: the warm-up iterations before the capture take real optimiser steps (on whatever sits in the
+        # static input buffer); `train` must not see them -- parameters and optimiser state are put back afterwards
+        saved = self._snapshot() if preserve_state else None
         self._capture(warmup)
+        if saved is not None:
+            self._restore(saved)
+
+    def set_alpha(self, alpha: float) -> None:
+        """New fade-in weight for the following replays (one asynchronous scalar write on the current stream)."""
+        if alpha != self._alpha_host:
+            self.alpha.fill_(float(alpha))
+            self._alpha_host = float(alpha)
 
     # -- the two step bodies (static shapes, no host sync) -------------------------------------------------
     def _critic_body(self):
@@ -73,10 +90,7 @@ class GraphedSteps:
             grads_w = th.autograd.grad(d_loss, params, allow_unused=True)
             main.wait_stream(branch)
             grads = [gw if gg is None else (gg if gw is None else gw + gg) for gw, gg in zip(grads_w, grads_gp)]
-        for p, g in zip(params, grads):
-            p.grad = g
-        if self.sync_d is not None:
-            self.sync_d()
+        self._install(params, grads, self.bucket_d)
         self.od.step()
         return th.stack([d_loss.detach(), gp.detach(), out[:n].mean().detach(), out[n:].mean().detach()])
 
@@ -90,12 +104,40 @@ class GraphedSteps:
             out_fake = disc(gen(z, alpha), alpha)
             g_loss = networks.wasserstein_generator_loss(out_fake)
             grads = th.autograd.grad(g_loss, params, allow_unused=True)
-        for p, g in zip(params, grads):
-            p.grad = g
-        if self.sync_g is not None:
-            self.sync_g()
+        self._install(params, grads, self.bucket_g)
         self.og.step()
         return th.stack([g_loss.detach(), out_fake.mean().detach()])
+
+    @staticmethod
+    def _install(params, grads, bucket):
+        if bucket is None:
+            for p, g in zip(params, grads):
+                p.grad = g
+        else:
+            assert [id(p) for p in bucket.params] == [id(p) for p in params]
+            bucket.adopt(grads)
+
+    def _snapshot(self):
+        params = [p for m in (self.gen, self.disc) for p in m.parameters()]
+        state = {}
+        for opt in (self.og, self.od):
+            for p, st in opt.state.items():
+                state[id(p)] = {k: (v.clone() if th.is_tensor(v) else v) for k, v in st.items()}
+        return [p.detach().clone() for p in params], state
+
+    def _restore(self, saved):
+        values, state = saved
+        params = [p for m in (self.gen, self.disc) for p in m.parameters()]
+        with th.no_grad():
+            for p, v in zip(params, values):
+                p.copy_(v)                           # in place: the graphs hold the storages
+            for opt in (self.og, self.od):
+                for p, st in opt.state.items():
+                    old = state.get(id(p))
+                    for k, v in st.items():
+                        if th.is_tensor(v):
+                            v.copy_(old[k]) if old is not None else v.zero_()
+        ops.invalidate_pack_cache()
 
     def _capture(self, warmup: int):
         side = th.cuda.Stream()

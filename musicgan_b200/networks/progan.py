@@ -25,6 +25,14 @@ def _conv3(cin: int, cout: int) -> nn.Conv2d:
     return nn.Conv2d(cin, cout, kernel_size=(3, 3), stride=(1, 1), padding=(1, 1))
 
 
+def _blend(old: th.Tensor, new: th.Tensor, alpha) -> th.Tensor:
+    """alpha * new + (1 - alpha) * old (generator.py:124, discriminator.py:113) as ONE kernel: old + alpha * (new - old).
+    `alpha` is the reference's Python float or a 0-dim device tensor (graphed.py feeds it to captured graphs that way)."""
+    if th.is_tensor(alpha):
+        alpha = alpha.to(dtype=old.dtype)
+    return th.lerp(old, new.to(old.dtype), alpha)
+
+
 def _require_cuda(t: th.Tensor, who: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"{who}: musicgan_b200 networks run on a CUDA (sm_100a) device only -- call .cuda() "
@@ -105,7 +113,7 @@ class Generator(nn.Module):
         if self.__last_end_block is None:
             return new_mp
         # alpha * new + (1 - alpha) * old (generator.py fade-in) as ONE kernel: old + alpha * (new - old)
-        return th.lerp(self.__last_end_block(out), new_mp, alpha)
+        return _blend(self.__last_end_block(out), new_mp, alpha)
 
     def next_layer(self) -> bool:
         if not self.growing:
@@ -184,8 +192,7 @@ class Discriminator(nn.Module):
         _require_cuda(x, "Discriminator.forward")
         out = self.__conv_blocks[self.__curr_layer](self.__start_block(x))
         if self.__last_start_block is not None:
-            old = self.__last_start_block(x)
-            out = th.lerp(old, out.to(old.dtype), alpha)       # alpha * out + (1 - alpha) * old, one kernel, one rounding
+            out = _blend(self.__last_start_block(x), out, alpha)
         for i in range(self.__curr_layer + 1, len(self.__conv_blocks)):
             out = self.__conv_blocks[i](out)
         return self.__clf(out.flatten(1, -1).float())

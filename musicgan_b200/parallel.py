@@ -47,38 +47,63 @@ def dataset_shard_plan(sample_counts: Sequence[int], rank: int, world_size: int,
 
 
 class FlatGradBucket:
-    """Gradients of a parameter list viewed as one flat fp32 buffer: `sync()` copies the existing .grad tensors in,
-    all-reduces once, scales by 1/world and copies back.  Parameters whose .grad is None (blocks not yet reached by
-    the progressive growing) are skipped on every rank alike, so they stay None and Adam keeps ignoring them -- the
-    set of active parameters is a function of the growth stage only, identical on all ranks."""
+    """Gradients of a parameter list living in ONE flat fp32 buffer: `adopt(grads)` gathers freshly computed gradient
+    tensors into the buffer with one multi-tensor copy, all-reduces the buffer once (averaging inside NCCL), and installs
+    VIEWS of the buffer as the parameters' .grad -- nothing is copied back.  Parameters whose gradient is None (blocks not
+    yet reached by the progressive growing) are skipped on every rank alike, so they stay None and Adam keeps ignoring them
+    -- the set of active parameters is a function of the growth stage only, identical on all ranks.
+
+    `sync()` is the same for gradients that already sit in .grad (eager `backward()`)."""
 
     def __init__(self, params: Iterable[th.nn.Parameter]):
         self.params: List[th.nn.Parameter] = [p for p in params]
         self._flat = None
+        self._views = None
+        self._key = None
 
     def rebuild(self, params: Iterable[th.nn.Parameter]) -> None:       # after next_layer() / add_param_group
         self.params = [p for p in params]
-        self._flat = None
+        self._flat = self._views = self._key = None
+
+    def _layout(self, active: List[th.nn.Parameter]):
+        key = tuple(id(p) for p in active)
+        if key != self._key:
+            n = sum(p.numel() for p in active)
+            self._flat = th.empty(n, dtype=th.float32, device=active[0].device)
+            self._views, off = [], 0
+            for p in active:
+                self._views.append(self._flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            self._key = key
+        return self._flat, self._views
+
+    def adopt(self, grads: Sequence) -> int:
+        """`grads[i]` is the new gradient of `params[i]` or None.  Returns the number of all-reduced elements."""
+        rank, ws = world()
+        pairs = [(p, g) for p, g in zip(self.params, grads) if g is not None]
+        for p, g in zip(self.params, grads):
+            if g is None:
+                p.grad = None
+        if not pairs:
+            return 0
+        if ws == 1:
+            for p, g in pairs:
+                p.grad = g
+            return 0
+        flat, views = self._layout([p for p, _ in pairs])
+        th._foreach_copy_(views, [g.to(th.float32) for _, g in pairs])
+        _all_reduce_mean(flat, ws)
+        for (p, _), v in zip(pairs, views):
+            p.grad = v
+        return flat.numel()
 
     def sync(self) -> int:
-        rank, ws = world()
-        active = [p for p in self.params if p.grad is not None]
-        if ws == 1 or not active:
-            return 0
-        n = sum(p.grad.numel() for p in active)
-        if self._flat is None or self._flat.numel() < n or self._flat.device != active[0].grad.device:
-            self._flat = th.empty(n, dtype=th.float32, device=active[0].grad.device)
-        flat = self._flat[:n]
-        off = 0
-        for p in active:
-            k = p.grad.numel()
-            flat[off:off + k].copy_(p.grad.reshape(-1))
-            off += k
+        return self.adopt([p.grad for p in self.params])
+
+
+def _all_reduce_mean(flat: th.Tensor, ws: int) -> None:
+    if flat.is_cuda:
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)          # NCCL averages in the collective: no scaling kernel
+    else:                                                   # gloo (CPU tests) has no AVG
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         flat.mul_(1.0 / ws)
-        off = 0
-        for p in active:
-            k = p.grad.numel()
-            p.grad.copy_(flat[off:off + k].view_as(p.grad))
-            off += k
-        return n

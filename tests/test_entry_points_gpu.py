@@ -59,18 +59,27 @@ def test_generate_writes_clips_of_the_reference_length(tmp_path):
         assert sr == 44100 and tuple(w.shape) == (1, 256 * (512 * 2 - 1)) and torch.isfinite(w).all()
 
 
-def test_train_runs_grows_and_checkpoints(tmp_path):
+@pytest.mark.parametrize("cuda_graphs", [True, False])
+def test_train_runs_grows_and_checkpoints(tmp_path, cuda_graphs):
+    """`train` on the CUDA-graph path (the object bench.py times) through TWO growth events -- re-capture at each
+    next_layer(), alpha ramping as a device scalar -- and on the eager path; checkpoints follow the reference's schedule
+    (utils.py:209-233: first files at call #save_every)."""
     import musicgan_b200 as mg
     ds, out = tmp_path / "ds", tmp_path / "run"
     ds.mkdir()
     g = torch.Generator().manual_seed(1)
     for i in range(8):
         torch.save(torch.rand(2, 512, 512, generator=g, dtype=torch.float64) * 2 - 1, str(ds / f"magn_phase_{i}.pt"))
-    mg.train("t", str(ds), str(out), batch_size=4, nb_epoch=2, num_workers=0, save_every=3, max_iterations=4, seed=0)
+    mg.train("t", str(ds), str(out), batch_size=4, nb_epoch=8, num_workers=0, save_every=3, max_iterations=9, seed=0,
+             cuda_graphs=cuda_graphs, log_every=2, train_lengths=(8, 12, 150000, 200000, 250000, 300000, 350000),
+             fadein_lengths=(1, 16, 16, 50000, 62500, 75000, 87500, 100000))
     saved = sorted(os.listdir(out))
-    assert "gen_0.pt" in saved and "disc_1.pt" in saved and "optim_gen_0.pt" in saved
-    sd = torch.load(str(out / "gen_0.pt"))
-    assert "_Generator__gen_blocks.0.0.weight" in sd and all(torch.isfinite(v).all() for v in sd.values())
+    assert {"gen_0.pt", "disc_1.pt", "optim_gen_2.pt"} <= set(saved) and "gen_3.pt" not in saved
+    sd0, sd2 = torch.load(str(out / "gen_0.pt")), torch.load(str(out / "gen_2.pt"))
+    assert "_Generator__gen_blocks.0.0.weight" in sd0 and all(torch.isfinite(v).all() for v in sd2.values())
+    # grown twice by iteration 9 (12 and 24 samples seen): the end block now maps the 96 channels of block 2
+    assert tuple(sd2["_Generator__end_block.0.weight"].shape) == (2, 96, 1, 1)
+    assert not torch.equal(sd0["_Generator__gen_blocks.0.0.weight"], sd2["_Generator__gen_blocks.0.0.weight"])      # it trains
 
 
 def test_device_prefetcher_order_and_content():
