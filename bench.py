@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the MusicGAN hot path on N B200s (one process per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload transform|inverse|train]
-                    [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload both|transform|train|sweep|generate]
+                    [--batch B] [--stage S] [--nb-vec V] [--impl b200|reference|torch_cuda]
 
 Prints ONE JSON line (rank 0).  Workloads (BASELINE.json configs):
   transform  config 1 scaled to a batch: `--clips` 60 s mono clips per GPU resident in HBM; a step is
@@ -10,6 +10,11 @@ Prints ONE JSON line (rank 0).  Workloads (BASELINE.json configs):
   train      config 2 (HEADLINE): one WGAN-GP iteration of the reference schedule at 512x512, batch 8 per GPU:
              a critic step every iteration, a generator step every 5th (train.py:189), Adam updates included; steps/s.
   both       default: the train line, with the transform line nested under "secondary".
+  sweep      config 3: the same iteration at every stage 0..7 of the progressive schedule (`--batch 64`), alpha 0.5 / 1.0.
+  train --batch 64 under torchrun = config 4 (64 samples per GPU, one flat-bucket all-reduce per optimiser step; `--stage 3`
+             for the 32 x 32 stage).
+  generate   config 5: G inference on a wide latent + inverse transform, `--gen-clips` clips per GPU, `--nb-vec` 4 | 10.
+`--impl torch_cuda` times the reference's modules through stock torch (cuDNN / cuFFT) on the same GPU: the bar on the box.
 
 `value` is timed with inputs resident in HBM; `e2e` goes through the public Python API with pinned-host
 inputs and a device->host read of the step's result inside the timed region.  `--impl reference` times the
@@ -198,6 +203,17 @@ def run_transform(args, rank, world, local):
         achieved = frames_per_step * BYTES_PER_FRAME / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
         step_gbs = frames_per_step * BYTES_PER_FRAME * args.steps / (ms * 1e-3) / 1e9
         cpu_v, cpu_n, cpu_el = cpu_transform_baseline(args.cpu_seconds)
+        torch_arm = None
+        if world == 1:
+            from baseline import torch_b200 as tb
+            torch.cuda.empty_cache()
+            try:
+                tv, tms = tb.time_transform(16, N_60S, 3, 2)
+                torch_arm = {"value": tv, "unit": "frames/s", "ms_per_step": tms, "clips_per_step": 16,
+                             "what": "torch-CUDA restatement of wav_to_stft + stft_to_phase_magn (cuFFT + ATen, cumsum in double), "
+                                     "batched over 16 clips, inputs resident"}
+            except Exception as e:      # noqa: BLE001
+                torch_arm = {"error": f"{type(e).__name__}: {str(e)[:120]}"}
         res = {
             "metric": "spectrogram frames/s (STFT+IF)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -216,6 +232,7 @@ def run_transform(args, rank, world, local):
                          "kernel_ms": {k: round(v[0] / max(v[1], 1), 4) for k, v in prof.items()}},
             "cpu_baseline": {"value": cpu_v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": f"{cpu_n} x 60 s clip (oracle port of wav_to_stft + stft_to_phase_magn) in {cpu_el:.1f} s"},
+            "torch_b200": torch_arm,
         }
     return res
 
@@ -249,9 +266,28 @@ def run_transform_reference(args, rank):
 # ------------------------------------------------------------------------------------------------
 # generate workload (BASELINE config 5): G inference on a wide latent + inverse transform, clips sharded over the ranks
 # ------------------------------------------------------------------------------------------------
+def cpu_generate_baseline(nb_vec: int, n_clips: int = 4):
+    """Oracle port of generate.py:47-65 on the host cores: G forward on the wide latent (fp32) + per-clip inverse transform."""
+    from oracle import audio_oracle as ao, networks_oracle as no
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd_g = no.make_state("gen", 7, 1)
+    g = torch.Generator().manual_seed(0)
+    z = torch.randn(n_clips, 32, 2, 2 * nb_vec, generator=g)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        img = torch.cat([no.gen_forward(sd_g, z[i:i + 1], 1.0, 7) for i in range(n_clips)])
+    t1 = time.perf_counter()
+    for i in range(n_clips):
+        ao.magn_phase_to_wav(img[i:i + 1].clone())
+    t2 = time.perf_counter()
+    return {"value": n_clips / (t2 - t0), "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_clips} clips of {512 * nb_vec} frames: G forward {t1 - t0:.1f} s + inverse transform {t2 - t1:.1f} s"}
+
+
 def run_generate(args, rank, world, local):
     from musicgan_b200 import _lib, audio, networks
-    nb_vec, per_gpu, sub = 4, args.gen_clips, 16
+    nb_vec, per_gpu = args.nb_vec, args.gen_clips
+    sub = min(per_gpu, max(1, 128 // nb_vec))          # 128 x 512 frame-columns per sub-batch: >= 148 CTAs in every inverse kernel
     torch.manual_seed(0)
     gen = networks.Generator(32, end_layer=7).eval().cuda()
     z_all = torch.randn(per_gpu, 32, 2, 2 * nb_vec, device="cuda")
@@ -283,15 +319,16 @@ def run_generate(args, rank, world, local):
         "metric": "generated clips/s (G inference + IF->phase->iSTFT)", "value": value, "unit": "clips/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16 (G) / f32 (inverse)", "data": "synthetic",
-        "config": {"workload": f"generate (BASELINE config 5): {per_gpu} clips/GPU/step of {512 * nb_vec} frames (11.9 s), sub-batches of {sub}",
-                   "parallelism": f"clips sharded over {world} GPU(s), no collective"},
+        "config": {"workload": f"generate (BASELINE config 5): {per_gpu} clips/GPU/step of {512 * nb_vec} frames "
+                               f"({256 * (512 * nb_vec - 1) / 44100:.1f} s), nb_vec {nb_vec}, sub-batches of {sub}",
+                   "clips_total": per_gpu * world, "parallelism": f"clips sharded over {world} GPU(s), no collective"},
         "clocks": cs.summary(),
         "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": per_gpu * 256 * (512 * nb_vec - 1) * 4},
         "gpu_launches": int(sum(c for _, c in prof.values())),
         "roofline": {"bound": "hbm", "kernel": "inverse transform kernels (k_inv_* + k_istft)", "achieved": achieved, "peak": pk["hbm"],
                      "unit": "GB/s", "frac": achieved / pk["hbm"], "peak_source": pk["src"], "traffic": None,
                      "kernel_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}},
-        "cpu_baseline": None,
+        "cpu_baseline": cpu_generate_baseline(nb_vec, 4),
     }
 
 
@@ -300,12 +337,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("MG_BENCH_WORKLOAD", "both"), choices=["both", "transform", "train", "generate"],
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_cuda"])
+    ap.add_argument("--workload", default=os.environ.get("MG_BENCH_WORKLOAD", "both"), choices=["both", "transform", "train", "generate", "sweep"],
                     help="both (default): the train workload (BASELINE config 2) is the headline line, the transform workload "
                          "(config 1) rides along under 'secondary'")
     ap.add_argument("--clips", type=int, default=64, help="clips per GPU per step (transform workload)")
-    ap.add_argument("--batch", type=int, default=8, help="samples per GPU per step (train workload)")
+    ap.add_argument("--batch", type=int, default=8, help="samples per GPU per step (train / sweep workloads; 64 = BASELINE configs 3 and 4)")
+    ap.add_argument("--stage", type=int, default=7, help="growth stage of the train workload (7 = 512 x 512)")
+    ap.add_argument("--nb-vec", type=int, default=4, help="512-frame images per generated clip (generate workload; CLI default of the reference: 10)")
     ap.add_argument("--e2e-clips", type=int, default=16)
     ap.add_argument("--gen-clips", type=int, default=128, help="clips per GPU per step (generate workload)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -321,6 +360,19 @@ def main():
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
+    if args.impl == "torch_cuda":
+        rank = int(os.environ.get("RANK", "0"))
+        if rank == 0:
+            torch.cuda.set_device(0)
+            from musicgan_b200 import bench_train
+            res = bench_train.run_torch_cuda(args, rank, ClockSampler, 0)
+            if args.workload in ("both", "transform"):
+                from baseline import torch_b200 as tb
+                tv, tms = tb.time_transform(16, N_60S, max(3, min(args.steps, 10)), 2)
+                res["secondary"] = {"impl": "torch_cuda", "metric": "spectrogram frames/s (STFT+IF)", "value": tv, "unit": "frames/s",
+                                    "ms_per_step": tms, "config": {"workload": "create_dataset transform, 16 x 60 s clips per step, stock torch on the GPU"}}
+            emit(res)
+        return
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
         res = None
@@ -341,6 +393,9 @@ def main():
     res = None
     if args.workload == "generate":
         res = run_generate(args, rank, world, local)
+    if args.workload == "sweep":
+        from musicgan_b200 import bench_train
+        res = bench_train.run_sweep(args, rank, world, local, timed_region, ClockSampler, peaks)
     if args.workload in ("both", "train"):
         from musicgan_b200 import bench_train
         res = bench_train.run(args, rank, world, local, timed_region, ClockSampler, peaks)

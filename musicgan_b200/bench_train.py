@@ -11,9 +11,15 @@ import time
 
 import torch as th
 
-FLOP_D_STEP = 121.78e9     # per sample at stage 7: 3 F_G + 12 F_D  (FlopCounterMode on the reference)
-FLOP_G_STEP = 48.71e9      # 3 F_G + 3 F_D
-FLOP_PER_ITER = FLOP_D_STEP + FLOP_G_STEP / 5.0
+# algorithmic GFLOP per sample of the reference's critic step (3 F_G + 12 F_D) and generator step (3 F_G + 3 F_D) at each
+# stage of the progressive schedule (FlopCounterMode on the reference)
+GFLOP_D_STEP = [0.111, 0.430, 1.391, 4.156, 11.601, 29.76, 67.233, 121.78]
+GFLOP_G_STEP = [0.030, 0.158, 0.543, 1.649, 4.627, 11.89, 26.884, 48.71]
+
+
+def flop_per_iter(stage: int) -> float:
+    """one reference iteration = critic step + 1/5 generator step (train.py:189)"""
+    return (GFLOP_D_STEP[stage] + GFLOP_G_STEP[stage] / 5.0) * 1e9
 
 
 def _build(stage: int, seed: int, device):
@@ -29,7 +35,7 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
     from . import _lib, train_step
     from .networks import ops
     dev = th.device("cuda", local)
-    stage, batch, alpha = 7, args.batch, 0.5
+    stage, batch, alpha = args.stage, args.batch, 0.5
     gen, disc = _build(stage, 0, dev)
     use_graphs = bool(int(os.environ.get("MG_GRAPHS", "1")))
     opt_g = th.optim.Adam(gen.parameters(), lr=1e-3, betas=(0.0, 0.9), capturable=use_graphs, fused=True)
@@ -135,7 +141,7 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
     if rank != 0:
         return None
     pk = peaks()
-    conv_names = ("k_conv3x3_fprop", "k_conv3x3_dgrad", "k_conv3x3_wgrad")
+    conv_names = ("k_conv3x3_fprop", "k_conv3x3_dgrad", "k_conv3x3_wgrad", "k_conv3x3_split_fprop", "k_conv3x3_split_dgrad")
     conv_ms = sum(prof.get(n, (0.0, 0))[0] for n in conv_names)
     conv_launches = sum(prof.get(n, (0.0, 0))[1] for n in conv_names)
     conv_s = conv_ms * 1e-3
@@ -148,14 +154,16 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
     t_hbm = conv_bytes_timed / (pk["hbm"] * 1e9)
     t_bound = sum(max(f / (pk["tf_sus"] * 1e12), b / (pk["hbm"] * 1e9)) for f, b in conv_launch_list) * scale
     hbm_bound = t_hbm >= t_tensor
-    step_tf = batch * FLOP_PER_ITER * args.steps / (ms * 1e-3) / 1e12
-    cpu = cpu_baseline(batch)
+    step_tf = batch * flop_per_iter(stage) * args.steps / (ms * 1e-3) / 1e12
+    cpu = cpu_baseline(batch, stage=stage, budget_s=args.cpu_seconds * 2)
+    torch_arm = torch_b200_numbers(stage, batch) if world == 1 else None
     return {
         "metric": "GAN train steps/s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "ProGAN WGAN-GP iteration at 512x512 (BASELINE config 2): critic step every iteration + generator "
-                               "step every 5th, Adam updates included, alpha 0.5 (both fade paths)", "batch_per_gpu": batch,
+        "config": {"workload": f"ProGAN WGAN-GP iteration at {res}x{res} (BASELINE config {2 if batch == 8 and stage == 7 else 4}): critic step "
+                               "every iteration + generator step every 5th, Adam updates included, alpha 0.5 (both fade paths)",
+                   "stage": stage, "batch_per_gpu": batch,
                    "global_batch": batch * world, "l2": "activations of one step (>1 GB) exceed L2; 4 rotating real batches",
                    "parallelism": f"dp{world}" + (" flat-bucket NCCL all-reduce" if world > 1 else ""),
                    "cuda_graphs": use_graphs},
@@ -178,41 +186,160 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
                      "step_algorithmic_tflops": step_tf, "step_frac": step_tf / pk["tf_sus"],
                      "kernel_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}},
         "cpu_baseline": cpu,
+        "torch_b200": torch_arm,
+        "samples_per_s": value * batch,
     }
 
 
-def cpu_baseline(batch: int):
-    """Oracle port of the reference step body (fp32, all host threads): one critic step + one generator step at
-    512 x 512, batch `batch`; value = 1 / (t_critic + t_generator / 5)."""
+def torch_b200_numbers(stage: int, batch: int, steps: int = 5, warmup: int = 3):
+    """The reference's modules through stock torch on this GPU (cuDNN): the bar on the same box."""
+    import gc
+    from baseline import torch_b200 as tb
+    th.cuda.empty_cache()
+    out = {"what": "stock torch (cuDNN / ATen) restatement of the reference modules and step body, same iteration schedule, "
+                   "inputs resident, CUDA events", "unit": "steps/s", "batch": batch, "stage": stage}
+    for mode in ("fp32", "bf16_autocast_channels_last"):
+        try:
+            v, ms = tb.time_train(stage, batch, mode, steps, warmup)
+            out[mode] = {"value": v, "ms_per_step": ms}
+        except Exception as e:      # noqa: BLE001  (e.g. out of memory at batch 64: reported, not fatal)
+            out[mode] = {"error": f"{type(e).__name__}: {str(e)[:120]}"}
+        gc.collect(); th.cuda.empty_cache()
+    return out
+
+
+def cpu_baseline(batch: int, stage: int = 7, steps: int = 1, warmup: int = 0, budget_s: float = 30.0):
+    """Oracle port of the reference step body (fp32, all host threads) at the reference's full cost (fake batch attached in
+    the critic step, critic gradients computed in the generator step): `steps` iterations of the reference schedule --
+    a critic step each, a generator step every 5th -- after `warmup` full-size iterations.
+    value = iterations per second with the generator step weighted 1/5."""
     from oracle import networks_oracle as no
     th.set_num_threads(os.cpu_count() or 1)
-    stage, alpha = 7, 0.5
+    alpha, res = 0.5, 4 * 2 ** stage
     sd_g, sd_d = no.make_state("gen", stage, 1), no.make_state("disc", stage, 2)
     g = th.Generator().manual_seed(0)
     z = th.randn(batch, 32, 2, 2, generator=g)
-    x_real = th.rand(batch, 2, 512, 512, generator=g) * 2 - 1
+    x_real = th.rand(batch, 2, res, res, generator=g) * 2 - 1
     eps = th.rand(batch, 1, 1, 1, generator=g)
-    no.d_step(sd_g, sd_d, z[:1], x_real[:1], eps[:1], alpha, stage)      # warm-up (thread pools, allocator) on one sample
-    t0 = time.perf_counter()
-    no.d_step(sd_g, sd_d, z, x_real, eps, alpha, stage)
-    t1 = time.perf_counter()
-    no.g_step(sd_g, sd_d, z, alpha, stage)
-    t2 = time.perf_counter()
-    v = 1.0 / ((t1 - t0) + (t2 - t1) / 5.0)
-    return {"value": v, "unit": "steps/s", "cores": th.get_num_threads(), "kind": "port",
-            "sample": f"1 critic step ({t1 - t0:.1f} s) + 1 generator step ({t2 - t1:.1f} s), batch {batch}, fp32"}
+    no.d_step(sd_g, sd_d, z[:1], x_real[:1], eps[:1], alpha, stage, attached=True)      # thread pools, allocator
+    for _ in range(warmup):
+        no.d_step(sd_g, sd_d, z, x_real, eps, alpha, stage, attached=True)
+    t_d, t_g, n_d, n_g = 0.0, 0.0, 0, 0
+    for i in range(steps):
+        t0 = time.perf_counter()
+        no.d_step(sd_g, sd_d, z, x_real, eps, alpha, stage, attached=True)
+        t1 = time.perf_counter()
+        t_d += t1 - t0; n_d += 1
+        if i % 5 == 0:
+            no.g_step(sd_g, sd_d, z, alpha, stage, critic_grads=True)
+            t_g += time.perf_counter() - t1; n_g += 1
+        if t_d + t_g > budget_s:
+            break
+    v = 1.0 / (t_d / n_d + (t_g / n_g) / 5.0)
+    return {"value": v, "unit": "steps/s", "cores": th.get_num_threads(), "kind": "port", "steps_run": n_d,
+            "sample": f"{n_d} critic step(s) ({t_d / n_d:.2f} s each) + {n_g} generator step(s) ({t_g / n_g:.2f} s each) after {warmup} "
+                      f"full-size warm-up(s), {res}x{res}, batch {batch}, fp32, reference's full cost (attached fake batch)"}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return None
-    batch = args.batch
-    cpu = cpu_baseline(batch)
+    batch, stage = args.batch, args.stage
+    res = 4 * 2 ** stage
+    cpu = cpu_baseline(batch, stage=stage, steps=max(1, args.steps), warmup=max(0, args.warmup), budget_s=240.0)
     return {
         "impl": "reference", "metric": "GAN train steps/s", "value": cpu["value"], "unit": "steps/s", "n_gpus": args.gpus,
-        "steps": 1, "warmup": 0, "ms_per_step": 1e3 / cpu["value"], "higher_is_better": True, "scaling": "weak",
+        "steps": cpu["steps_run"], "warmup": args.warmup, "ms_per_step": 1e3 / cpu["value"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ProGAN WGAN-GP iteration at 512x512 (BASELINE config 2) on the host CPU", "batch_per_gpu": batch},
+        "config": {"workload": f"ProGAN WGAN-GP iteration at {res}x{res} (BASELINE config {2 if batch == 8 and stage == 7 else 4}) on the host "
+                               "CPU: oracle port of the reference step body, critic step every iteration + generator step every 5th",
+                   "stage": stage, "batch_per_gpu": batch, "time_budget_s": 240},
         "cpu_baseline": cpu,
         "e2e": {"value": cpu["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def run_torch_cuda(args, rank, ClockSampler, local):
+    """`--impl torch_cuda`: the stock-torch arm as a line of its own (bf16 autocast + channels_last = its best setting)."""
+    if rank != 0:
+        return None
+    from baseline import torch_b200 as tb
+    batch, stage = args.batch, args.stage
+    res = 4 * 2 ** stage
+    with ClockSampler(local) as cs:
+        nums = torch_b200_numbers(stage, batch, steps=max(3, args.steps), warmup=max(3, args.warmup))
+    best = max((m for m in ("fp32", "bf16_autocast_channels_last") if "value" in nums[m]), key=lambda m: nums[m]["value"])
+    return {
+        "impl": "torch_cuda", "metric": "GAN train steps/s", "value": nums[best]["value"], "unit": "steps/s", "n_gpus": 1,
+        "steps": max(3, args.steps), "warmup": max(3, args.warmup), "ms_per_step": nums[best]["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if best.startswith("bf16") else "f32 (cuDNN TF32 default)", "data": "synthetic",
+        "config": {"workload": f"ProGAN WGAN-GP iteration at {res}x{res} through stock torch on the GPU ({best})", "stage": stage, "batch_per_gpu": batch},
+        "clocks": cs.summary(), "torch_b200": nums, "gpu_launches": 0,
+    }
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE config 3: the progressive-growing sweep, every stage at a fixed batch
+# ------------------------------------------------------------------------------------------------------------------
+def run_sweep(args, rank, world, local, timed_region, ClockSampler, peaks):
+    from . import parallel
+    from .graphed import GraphedSteps
+    dev = th.device("cuda", local)
+    batch = args.batch
+    pk = peaks()
+    rows = []
+    th.cuda.manual_seed(1000 + rank)
+    with ClockSampler(local) as cs:
+        for stage in range(8):
+            gen, disc = _build(stage, 0, dev)
+            opt_g = th.optim.Adam(gen.parameters(), lr=1e-3, betas=(0.0, 0.9), capturable=True, fused=True)
+            opt_d = th.optim.Adam(disc.parameters(), lr=1e-3, betas=(0.0, 0.9), capturable=True, fused=True)
+            bucket_d = parallel.FlatGradBucket(disc.parameters()) if world > 1 else None
+            bucket_g = parallel.FlatGradBucket(gen.parameters()) if world > 1 else None
+            res = 4 * 2 ** stage
+            reals = [th.rand(batch, 2, res, res, device=dev) * 2 - 1 for _ in range(4)]
+            graphed = GraphedSteps(gen, disc, opt_g, opt_d, batch, 32, res, 0.5, bucket_d=bucket_d, bucket_g=bucket_g)
+            it = [0]
+
+            def step():
+                graphed.critic_step(reals[it[0] % 4])
+                if it[0] % 5 == 0:
+                    graphed.generator_step()
+                it[0] += 1
+
+            for alpha in ((1.0,) if stage == 0 else (0.5, 1.0)):
+                graphed.set_alpha(alpha)
+                it[0] = 0
+                steps = args.steps if stage >= 5 else 4 * args.steps      # sub-millisecond stages: more steps per timing
+                ms = timed_region(step, steps, args.warmup, world)
+                sps = world * steps / (ms * 1e-3)
+                tf = batch * flop_per_iter(stage) * sps / 1e12
+                rows.append({"stage": stage, "resolution": res, "alpha": alpha, "steps_per_s": sps, "ms_per_step": ms / steps,
+                             "samples_per_s": sps * batch, "algorithmic_tflops": tf, "frac_of_bf16_peak": tf / (pk["tf_sus"] * world),
+                             "regime": "launch / latency bound (whole step < 2 ms)" if ms / steps < 2.0 else "tensor / HBM"})
+            del graphed, gen, disc, opt_g, opt_d, reals
+            th.cuda.empty_cache()
+    if rank != 0:
+        return None
+    head = next(r for r in rows if r["stage"] == 7 and r["alpha"] == 0.5)
+    # CPU: batch 8, every stage once, scaled per sample to the sweep's batch (SURVEY 8d)
+    cpu_rows, t_total = [], 0.0
+    for stage in range(8):
+        c = cpu_baseline(8, stage=stage, steps=1, warmup=0)
+        cpu_rows.append({"stage": stage, "steps_per_s_at_this_batch": c["value"] * 8.0 / batch, "sample": c["sample"]})
+    return {
+        "metric": "GAN train steps/s", "value": head["steps_per_s"], "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"progressive-growing sweep (BASELINE config 3): one WGAN-GP iteration (critic + 1/5 generator step, Adam "
+                               f"included) at every stage 0..7, batch {batch} per GPU, alpha 0.5 and 1.0; headline value = stage 7, alpha 0.5",
+                   "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": f"dp{world}", "cuda_graphs": True,
+                   "l2": "stages >= 4: activations of a step exceed L2; stages <= 3 fit in L2 and are launch bound (said per row)"},
+        "clocks": cs.summary(), "stages": rows,
+        "e2e": None, "gpu_launches": None,
+        "roofline": {"bound": "tensor", "kernel": "whole iteration at stage 7 (algorithmic FLOPs of the reference step / time)",
+                     "achieved": head["algorithmic_tflops"], "peak": pk["tf_sus"] * world, "unit": "TFLOP/s",
+                     "frac": head["frac_of_bf16_peak"], "peak_source": pk["src"] + " (sustained)", "traffic": None},
+        "cpu_baseline": {"value": cpu_rows[7]["steps_per_s_at_this_batch"], "unit": "steps/s", "cores": th.get_num_threads(), "kind": "port",
+                         "sample": f"batch 8 per stage, scaled per sample to batch {batch}", "stages": cpu_rows},
     }

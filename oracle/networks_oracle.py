@@ -124,25 +124,31 @@ def _leaf(sd: SD) -> SD:
     return {k: v.clone().requires_grad_(True) for k, v in sd.items()}
 
 
-def d_step(sd_g: SD, sd_d: SD, z, x_real, eps, alpha: float, stage: int):
+def d_step(sd_g: SD, sd_d: SD, z, x_real, eps, alpha: float, stage: int, attached: bool = False):
     """train.py:143-174: losses and discriminator parameter gradients of one critic step (fake batch detached:
-    SURVEY B.7 shows D's gradients are bit-identical to the non-detached reference)."""
+    SURVEY B.7 shows D's gradients are bit-identical to the non-detached reference).  attached=True keeps the fake
+    batch in the graph like the reference does (the generator is back-propagated for nothing, train.py:152-174): same
+    gradients, the reference's full cost -- used by the timed CPU baseline."""
     d = _leaf(sd_d)
-    with torch.no_grad():
-        x_fake = gen_forward(sd_g, z, alpha, stage)
+    if attached:
+        x_fake = gen_forward(_leaf(sd_g), z, alpha, stage)
+    else:
+        with torch.no_grad():
+            x_fake = gen_forward(sd_g, z, alpha, stage)
     out_real, out_fake = disc_forward(d, x_real, alpha, stage), disc_forward(d, x_fake, alpha, stage)
     loss = -(out_real.mean() - out_fake.mean())                  # criterion.py:12-14
     gp = gradient_penalty(d, x_real, x_fake, alpha, stage, eps)
     (loss + gp).backward()
-    return dict(loss=loss.detach(), gp=gp.detach(), x_fake=x_fake, out_real=out_real.detach(), out_fake=out_fake.detach(),
+    return dict(loss=loss.detach(), gp=gp.detach(), x_fake=x_fake.detach(), out_real=out_real.detach(), out_fake=out_fake.detach(),
                 grads={k: v.grad for k, v in d.items()})
 
 
-def g_step(sd_g: SD, sd_d: SD, z, alpha: float, stage: int):
-    """train.py:191-213: generator loss and generator parameter gradients."""
+def g_step(sd_g: SD, sd_d: SD, z, alpha: float, stage: int, critic_grads: bool = False):
+    """train.py:191-213: generator loss and generator parameter gradients.  critic_grads=True also computes (and drops)
+    the critic's parameter gradients like the reference's backward() does -- the timed CPU baseline's full cost."""
     g = _leaf(sd_g)
     x_fake = gen_forward(g, z, alpha, stage)
-    out_fake = disc_forward(sd_d, x_fake, alpha, stage)
+    out_fake = disc_forward(_leaf(sd_d) if critic_grads else sd_d, x_fake, alpha, stage)
     loss = -out_fake.mean()                                      # criterion.py:17-18
     loss.backward()
     return dict(loss=loss.detach(), x_fake=x_fake.detach(), out_fake=out_fake.detach(), grads={k: v.grad for k, v in g.items()})
