@@ -145,6 +145,18 @@ int mg_conv3x3_split_pack_weights(const float* w_f32, int Cin, int Cout, int dgr
 int mg_conv3x3_split_f32(const float* x, const void* packed, const float* bias, float* y, void* y_bf16, float* inv_norm,
                          int B, int H, int W, int Cin, int Cout, int flags, mgStream stream);
 
+/* All packed copies of all weights of a network in one launch (a training step re-packs every 3x3 weight after each
+ * optimiser step).  Fill one record per packed copy on the host with mg_pack_job_fill (kind 0: the layout of
+ * mg_conv3x3_pack_weights(mode); kind 1: the layout of mg_conv3x3_split_pack_weights(dgrad = mode & 1); Cin / Cout as
+ * in those calls), upload the array once, then call mg_pack_weights_multi after every parameter update. */
+typedef struct mgPackJob {
+    const float* w;      /* fp32 master weight [Cout][Cin][3][3] (device) */
+    void* out;           /* packed buffer (device) */
+    int cout_fwd, cin_fwd, flip, nt, parts, kind, total, reserved;
+} mgPackJob;
+int mg_pack_job_fill(mgPackJob* job_host, const float* w_f32, void* packed, int Cin, int Cout, int kind, int mode);
+int mg_pack_weights_multi(const mgPackJob* jobs_dev, int n_jobs, int max_total, mgStream stream);
+
 /* Weight gradient of the same convolution: dw[co][ci][ky][kx] = sum_{b,y,x} dy[b][y][x][co] *
  * xin[b][y+ky-1][x+kx-1][ci]   (xin = x, or x read through a nearest x2 upsampling when upsample_in != 0).
  * dy [B][H][W][Cout] bf16, x [B][H(/2)][W(/2)][Cin] bf16, dw fp32 [Cout][Cin][3][3] OVERWRITTEN (deterministic

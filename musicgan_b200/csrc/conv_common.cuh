@@ -1,5 +1,6 @@
 // Tile geometry shared by the convolution kernels.
 #pragma once
+#include <cuda_bf16.h>
 namespace mg {
 constexpr int kTileH = 16;                       // output rows per tile   (= 16 eight-row core-matrix groups)
 constexpr int kTileW = 8;                        // output cols per tile   (= one core-matrix group)
@@ -18,5 +19,31 @@ struct FastDiv { unsigned long long m; };
 inline FastDiv make_fast_div(int d) { FastDiv f; f.m = ((1ull << 40) / (unsigned long long)d) + 1ull; return f; }
 #if defined(__CUDACC__)
 __device__ __forceinline__ int fast_div(int n, FastDiv f) { return (int)(((unsigned long long)(unsigned)n * f.m) >> 40); }
+
+// Weight packing of the split-operand kernel (conv_split.cu):
+// fp32 [Cout][Cin][3][3] -> split bf16 [K/16][tap][hi, lo][2 chunks][N][8]   (N, K = GEMM channel counts)
+//   transpose_flip = 0: B[n = co][k = ci] of tap (ky,kx) = w[co][ci][ky][kx]
+//   transpose_flip = 1: data gradient, B[n = ci][k = co] = w[co][ci][2-ky][2-kx]
+__device__ __forceinline__ void pack_weights_split_range(const float* __restrict__ w, int Cout, int Cin, int transpose_flip,
+                                                         __nv_bfloat16* __restrict__ out, int first, int stride) {
+    const int N = transpose_flip ? Cin : Cout, K = transpose_flip ? Cout : Cin;
+    const int total = 9 * N * K;                       // (hi, lo) pairs
+    for (int i = first; i < total; i += stride) {
+        int r = i;
+        const int e = r & 7; r >>= 3;
+        const int n = r % N; r /= N;
+        const int chunk = r & 1; r >>= 1;
+        const int tap = r % 9, cg = r / 9;
+        const int k = cg * 16 + chunk * 8 + e;
+        const int ky = tap / 3, kx = tap % 3;
+        const float v = transpose_flip ? w[(((size_t)k * Cin + n) * 3 + (2 - ky)) * 3 + (2 - kx)]
+                                       : w[(((size_t)n * Cin + k) * 3 + ky) * 3 + kx];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        // destination: [cg][tap][part][chunk][n][e]
+        const size_t base = ((size_t)(cg * 9 + tap) * 2) * 2 * N * 8;
+        out[base + ((size_t)(0 * 2 + chunk) * N + n) * 8 + e] = hi;
+        out[base + ((size_t)(1 * 2 + chunk) * N + n) * 8 + e] = lo;
+    }
+}
 #endif
 }  // namespace mg

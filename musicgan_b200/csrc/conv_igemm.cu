@@ -359,14 +359,12 @@ k_conv3x3(const ConvParams p) {
 //                                w'[ci][co][ky][kx] = w[co][ci][2-ky][2-kx]; n runs over ci, k over co.
 //   `n_out`, `k_in` are the GEMM N and K channel counts of the packed operand.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_pack_weights(const float* __restrict__ w, int Cout, int Cin, int transpose_flip, int Nt, int parts,
-                               __nv_bfloat16* __restrict__ out) {
+__device__ __forceinline__ void pack_weights_range(const float* __restrict__ w, int Cout, int Cin, int transpose_flip, int Nt, int parts,
+                                                   __nv_bfloat16* __restrict__ out, int first, int stride) {
     const int n_out = transpose_flip ? Cin : Cout, k_in = transpose_flip ? Cout : Cin;
     const int nch = k_in >> 3;
     const int total = 9 * n_out * k_in;
-    pdl_trigger();
-    pdl_wait();
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    for (int i = first; i < total; i += stride) {
         // destination order: slice, tap, chunk, n_local, e
         int r = i;
         const int e = r & 7; r >>= 3;
@@ -395,6 +393,25 @@ __global__ void k_pack_weights(const float* __restrict__ w, int Cout, int Cin, i
     }
 }
 
+__global__ void k_pack_weights(const float* __restrict__ w, int Cout, int Cin, int transpose_flip, int Nt, int parts,
+                               __nv_bfloat16* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
+    pack_weights_range(w, Cout, Cin, transpose_flip, Nt, parts, out, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+// All packed copies of all weights of a network in ONE launch (a training step re-packs ~40 tensors after every
+// optimiser step: as separate launches they cost more than the packing itself).  grid (blocks, n_jobs).
+__global__ void __launch_bounds__(256)
+k_pack_weights_multi(const mgPackJob* __restrict__ jobs) {
+    pdl_trigger();
+    pdl_wait();
+    const mgPackJob j = jobs[blockIdx.y];
+    const int first = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    if (j.kind == 0) pack_weights_range(j.w, j.cout_fwd, j.cin_fwd, j.flip, j.nt, j.parts, (__nv_bfloat16*)j.out, first, stride);
+    else pack_weights_split_range(j.w, j.cout_fwd, j.cin_fwd, j.flip, (__nv_bfloat16*)j.out, first, stride);
+}
+
 struct ConvPlan { int Nt, stages, tmem_cols, n_slices, occupancy, epi_warps, n_acc, acc_stride, mb, blk_stride, halo_pos, halo_pitch; size_t smem; };
 
 static ConvPlan plan_conv(int Cin, int Cout, bool need_full_n, int H = 0, int parts = 1) {
@@ -407,7 +424,7 @@ static ConvPlan plan_conv(int Cin, int Cout, bool need_full_n, int H = 0, int pa
     //    The packed weight layout depends on this choice only, never on the shape chosen in step 2.
     int Nt = 0;
     for (int stages = 2; stages >= 1 && !Nt; --stages)
-        for (int n = Cout; n >= 16; n -= 16)
+        for (int n = Cout; n >= (need_full_n ? Cout : 16); n -= 16)
             if ((size_t)9 * nch * n * 16 * parts + (size_t)stages * nch * kHaloPitch * 16 + (size_t)2 * n * 16 + 4096 + 1024 + 384 <= budget) { Nt = n; break; }
     if (!Nt || (need_full_n && Nt != Cout)) return pl;
     const size_t base = (size_t)9 * nch * Nt * 16 * parts + (size_t)2 * Nt * 16 + 4096 + 1024 + 384;   // weights, bias pseudo-tap, constant A tile, PixelNorm partials, barriers
@@ -475,6 +492,37 @@ int mg_conv3x3_pack_weights(const float* w_f32, int Cin, int Cout, int mode, voi
     const int fwd_cout = dgrad ? Cin : Cout, fwd_cin = dgrad ? Cout : Cin;
     launch_pdl(k_pack_weights, dim3((total + 255) / 256), dim3(256), 0, st, w_f32, fwd_cout, fwd_cin, dgrad ? 1 : 0, pl.Nt, parts, (__nv_bfloat16*)packed);
     return check_launch("k_pack_weights");
+}
+
+// Fill `jobs[i]` (host memory) for one packed copy: kind 0 = mg_conv3x3_pack_weights(mode), kind 1 =
+// mg_conv3x3_split_pack_weights(dgrad = mode & 1); Cin / Cout are those of the GEMM, as in the single-tensor calls.
+int mg_pack_job_fill(mgPackJob* job, const float* w_f32, void* packed, int Cin, int Cout, int kind, int mode) {
+    if (!job || !w_f32 || !packed) return MG_ERR_BAD_ARG;
+    if (Cin < 16 || Cout < 16 || (Cin & 15) || (Cout & 15) || Cin > 256 || Cout > 256) return MG_ERR_UNSUPPORTED;
+    const int dgrad = mode & 1;
+    job->w = w_f32; job->out = packed; job->kind = kind ? 1 : 0; job->flip = dgrad;
+    job->cout_fwd = dgrad ? Cin : Cout; job->cin_fwd = dgrad ? Cout : Cin;
+    job->parts = (!kind && (mode & 2)) ? 2 : 1;
+    job->nt = 0;
+    if (!kind) {
+        ConvPlan pl = plan_conv(Cin, Cout, (mode & 4) != 0, 0, job->parts);
+        if (pl.Nt == 0) return MG_ERR_UNSUPPORTED;
+        job->nt = pl.Nt;
+    }
+    job->total = 9 * Cin * Cout;
+    return MG_OK;
+}
+
+// `jobs_dev`: n_jobs mgPackJob records in DEVICE memory (filled on the host with mg_pack_job_fill and uploaded once: the
+// pointers of parameters and packed buffers do not change between optimiser steps); max_total = largest job->total.
+int mg_pack_weights_multi(const mgPackJob* jobs_dev, int n_jobs, int max_total, mgStream stream) {
+    if (!jobs_dev || n_jobs <= 0 || max_total <= 0) return MG_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope ps("k_pack_weights_multi", st);
+    int blocks = (max_total + 256 * 8 - 1) / (256 * 8);
+    if (blocks < 1) blocks = 1;
+    launch_pdl(k_pack_weights_multi, dim3(blocks, n_jobs), dim3(256), 0, st, jobs_dev);
+    return check_launch("k_pack_weights_multi");
 }
 
 size_t mg_conv3x3_workspace_bytes(int Cin, int Cout) {

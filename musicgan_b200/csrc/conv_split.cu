@@ -243,31 +243,11 @@ k_conv3x3_split(const SplitParams p) {
     if (warp == 8) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-// fp32 [Cout][Cin][3][3] -> split bf16 [Cin_k/16][tap][hi, lo][2 chunks][N][8]   (N, K = GEMM channel counts)
-//   transpose_flip = 0: B[n = co][k = ci] of tap (ky,kx) = w[co][ci][ky][kx]
-//   transpose_flip = 1: data gradient, B[n = ci][k = co] = w[co][ci][2-ky][2-kx]
 __global__ void k_pack_weights_split(const float* __restrict__ w, int Cout, int Cin, int transpose_flip,
                                      __nv_bfloat16* __restrict__ out) {
-    const int N = transpose_flip ? Cin : Cout, K = transpose_flip ? Cout : Cin;
-    const int total = 9 * N * K;                       // (hi, lo) pairs
     pdl_trigger();
     pdl_wait();
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        int r = i;
-        const int e = r & 7; r >>= 3;
-        const int n = r % N; r /= N;
-        const int chunk = r & 1; r >>= 1;
-        const int tap = r % 9, cg = r / 9;
-        const int k = cg * 16 + chunk * 8 + e;
-        const int ky = tap / 3, kx = tap % 3;
-        const float v = transpose_flip ? w[(((size_t)k * Cin + n) * 3 + (2 - ky)) * 3 + (2 - kx)]
-                                       : w[(((size_t)n * Cin + k) * 3 + ky) * 3 + kx];
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        // destination: [cg][tap][part][chunk][n][e]
-        const size_t base = ((size_t)(cg * 9 + tap) * 2) * 2 * N * 8;
-        out[base + ((size_t)(0 * 2 + chunk) * N + n) * 8 + e] = hi;
-        out[base + ((size_t)(1 * 2 + chunk) * N + n) * 8 + e] = lo;
-    }
+    pack_weights_split_range(w, Cout, Cin, transpose_flip, out, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 struct SplitPlan { int Nt, n_slices, stages, tmem_cols; unsigned stage_bytes; size_t smem; };

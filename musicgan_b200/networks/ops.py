@@ -26,6 +26,11 @@ SPLIT_W = os.environ.get("MG_SPLIT_W", "1") != "0"
 def is_precise(h_out: int) -> bool:
     return h_out <= PRECISE_MAX_RES
 
+class PackJob(ctypes.Structure):        # mgPackJob of include/musicgan_b200.h
+    _fields_ = [("w", c_void_p), ("out", c_void_p), ("cout_fwd", c_int), ("cin_fwd", c_int), ("flip", c_int), ("nt", c_int),
+                ("parts", c_int), ("kind", c_int), ("total", c_int), ("reserved", c_int)]
+
+
 _declared = False
 _ws_cache = {}
 # bench bookkeeping of the 3x3 convolution launches issued through this module: FLOPs (2 * B*H*W * 9*Cin*Cout per call),
@@ -66,6 +71,8 @@ def _l():
         l.mg_unpool2_lrelu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]
         l.mg_pool2_planes_f32.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]
         l.mg_conv3x3_pack_weights.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]
+        l.mg_pack_job_fill.argtypes = [ctypes.POINTER(PackJob), c_void_p, c_void_p, c_int, c_int, c_int, c_int]
+        l.mg_pack_weights_multi.argtypes = [c_void_p, c_int, c_int, c_void_p]
         l.mg_conv3x3_split_workspace_bytes.restype = c_size_t
         l.mg_conv3x3_split_workspace_bytes.argtypes = [c_int, c_int]
         l.mg_conv3x3_split_pack_weights.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]
@@ -142,15 +149,38 @@ def _packed_weights(w: th.Tensor, cin: int, cout: int, kind):
     return buf
 
 
+_multi_tables = {}
+
+
 def prepack(module) -> None:
-    """Refresh, on the current stream, every packed copy the parameters of `module` have been asked for so far (the
-    warm-up steps before a graph capture ask for all of them).  After this call the forward / data-gradient kernels only
-    READ the cached copies, so independent branches of a step may run on different streams (graphed.py)."""
+    """Refresh, on the current stream and in ONE launch, every packed copy the parameters of `module` have been asked for so
+    far (the warm-up steps before a graph capture ask for all of them).  After this call the forward / data-gradient kernels
+    only READ the cached copies, so independent branches of a step may run on different streams (graphed.py)."""
+    entries = []
     for p in module.parameters():
         cache = getattr(p, "_mg_packed", None)
         if cache and p.is_cuda and p.requires_grad:
-            for (kind, cin, cout) in list(cache.keys()):
-                _packed_weights(p, cin, cout, kind)
+            for key, (stamp, buf) in cache.items():
+                entries.append((p, key, buf))
+    if not entries:
+        return
+    l = _l()
+    dev = entries[0][0].device
+    ident = tuple((p.data_ptr(), buf.data_ptr(), key) for p, key, buf in entries)
+    hit = _multi_tables.get(id(module))
+    if hit is None or hit[0] != ident:
+        jobs = (PackJob * len(entries))()
+        for j, (p, (kind, cin, cout), buf) in zip(jobs, entries):
+            _lib.check(l.mg_pack_job_fill(ctypes.byref(j), p.data_ptr(), buf.data_ptr(), cin, cout, 1 if kind[0] == "split" else 0, kind[1]),
+                       "mg_pack_job_fill")
+        table = th.frombuffer(bytearray(bytes(jobs)), dtype=th.uint8).to(dev)
+        hit = (ident, table, len(entries), max(j.total for j in jobs))
+        _multi_tables[id(module)] = hit
+    _, table, n, max_total = hit
+    with th.cuda.device(dev):
+        _lib.check(l.mg_pack_weights_multi(table.data_ptr(), n, max_total, th.cuda.current_stream().cuda_stream), "mg_pack_weights_multi")
+    for p, key, buf in entries:
+        p._mg_packed[key] = ((p._version, p.data_ptr(), _pack_epoch[0]), buf)
 
 
 def _check_act(x: th.Tensor, name: str, dtype=None):

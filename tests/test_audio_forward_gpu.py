@@ -75,6 +75,27 @@ def test_stage3_end_to_end(name):
     assert _frac_within(gp, ref_p.numpy(), 0, 1e-3) >= 0.995
 
 
+def test_if_threshold_is_the_references_own_cpu_vs_cuda_discrepancy():
+    """the end-to-end IF agreement required of the CUDA path is 'no worse than reference-CPU vs
+    reference-through-torch-CUDA on the same box'.  The reference's transform restated with stock torch ops (cuFFT, ATen,
+    cumsum in double: baseline/torch_b200.py) is run on this GPU and compared with the CPU oracle; our kernels must agree
+    with the oracle at least as well (minus 0.2 % slack for run-to-run wrap flips).  This is where the fixed 0.98 of the
+    other end-to-end tests comes from (measured 0.99+ for both on B200)."""
+    from musicgan_b200 import audio
+    from baseline import torch_b200 as tb
+    for name in ("noise_3s", "tonal_6s"):
+        wav = cases.forward_wav(name)
+        mono = wav.mean(0)
+        ref_m, ref_p = ao.wav_to_magn_phase(mono)
+        t_m, t_p = tb.transform(mono[None].cuda())
+        o_m, o_p = audio.wav_to_magn_phase_batch(wav[None].cuda())
+        f_torch = _frac_within(t_p[0].cpu().numpy(), ref_p.numpy(), 1e-4, 1e-4)
+        f_ours = _frac_within(o_p[0].cpu().numpy(), ref_p.numpy(), 1e-4, 1e-4)
+        print(f"{name}: IF within rtol 1e-4 + atol 1e-4 of the CPU reference: stock torch-CUDA {f_torch:.5f}, this library {f_ours:.5f}")
+        assert f_ours >= min(f_torch, 0.999) - 2e-3, (f_ours, f_torch)
+        assert f_ours >= 0.98
+
+
 def test_batch_equals_single():
     """Clips of a batch are independent units: every clip of a batch == the clip run alone (bit exact)."""
     from musicgan_b200 import audio

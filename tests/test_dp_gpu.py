@@ -1,6 +1,7 @@
 """GPU (needs >= 2 devices; skipped otherwise): data-parallel critic step -- the gradients after the flat-bucket NCCL
-all-reduce on 2 ranks, each with half of the batch, equal the single-process gradients on the whole batch
-(no batch-coupled layer in D or G, losses are batch means)."""
+all-reduce on 2 ranks, each with half of the batch, equal the fp32 CPU ORACLE's gradients on the concatenated batch
+(oracle.networks_oracle: reference train.py:143-174 / discriminator.py:157-184; SURVEY 8e: no batch-coupled layer in D or
+G, losses are batch means), term by term at rel-L2 <= 1e-2 like the single-GPU parity tests."""
 import os
 
 import pytest
@@ -31,26 +32,39 @@ def _rank(rank, world, port, ret):
         x_fake = (torch.rand(batch, 2, r, r, generator=g) * 2 - 1).cuda()
         eps = torch.rand(batch, 1, 1, 1, generator=g).cuda()
 
-        def grads(sl):
-            disc.zero_grad()
-            loss = -(disc(x_real[sl], alpha).mean() - disc(x_fake[sl], alpha).mean())
-            gp = disc.gradient_penalty(x_real[sl], x_fake[sl], alpha, eps=eps[sl])
-            (loss + gp).backward()
-
+        terms = {
+            "real": (lambda sl: disc(x_real[sl], alpha).mean(), lambda d: no.disc_forward(d, x_real.cpu(), alpha, stage).mean()),
+            "gp": (lambda sl: disc.gradient_penalty(x_real[sl], x_fake[sl], alpha, eps=eps[sl]),
+                   lambda d: no.gradient_penalty(d, x_real.cpu(), x_fake.cpu(), alpha, stage, eps.cpu())),
+            "critic": (lambda sl: -(disc(x_real[sl], alpha).mean() - disc(x_fake[sl], alpha).mean())
+                       + disc.gradient_penalty(x_real[sl], x_fake[sl], alpha, eps=eps[sl]), None),
+        }
         b, e = parallel.shard_bounds(batch, rank, world)
-        grads(slice(b, e))
-        n = parallel.FlatGradBucket(disc.parameters()).sync()
-        assert n > 0
-        mine = {k: p.grad.clone() for k, p in disc.named_parameters() if p.grad is not None}
-        grads(slice(0, batch))              # single-process reference on the concatenated batch (same kernels)
-        num = den = 0.0
-        for k, p in disc.named_parameters():
-            if p.grad is None:
-                assert k not in mine
-                continue
-            num += (mine[k].double() - p.grad.double()).pow(2).sum().item()
-            den += p.grad.double().pow(2).sum().item()
-        ret[rank] = (num / max(den, 1e-300)) ** 0.5
+        bucket = parallel.FlatGradBucket(disc.parameters())
+        out = {}
+        for key, (ours, oracle) in terms.items():
+            disc.zero_grad()
+            ours(slice(b, e)).backward()             # this rank's shard only
+            n = bucket.sync()                        # average over the two ranks
+            assert n > 0
+            mine = {k: p.grad.clone() for k, p in disc.named_parameters() if p.grad is not None}
+            if oracle is not None:                   # the fp32 oracle on the WHOLE batch
+                d = no._leaf(sd_d)
+                oracle(d).backward()
+                ref = {k: v.grad for k, v in d.items() if v.grad is not None}
+            else:                                    # total: single process on the whole batch (cancelling terms: see test_networks_gpu)
+                disc.zero_grad()
+                ours(slice(0, batch)).backward()
+                ref = {k: p.grad.cpu() for k, p in disc.named_parameters() if p.grad is not None}
+            num = den = 0.0
+            for k, r in ref.items():
+                if k not in mine:
+                    assert float(r.abs().max()) == 0.0, k
+                    continue
+                num += (mine[k].double().cpu() - r.double()).pow(2).sum().item()
+                den += r.double().pow(2).sum().item()
+            out[key] = (num / max(den, 1e-300)) ** 0.5
+        ret[rank] = out
     finally:
         dist.destroy_process_group()
 
@@ -61,5 +75,7 @@ def test_two_rank_allreduced_gradients_equal_single_process():
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_rank, args=(2, 29600 + os.getpid() % 1000, ret), nprocs=2, join=True)
-    print("rel-L2 of 2-rank averaged grads vs single process:", dict(ret))
-    assert all(v <= 2e-3 for v in ret.values())       # same bf16 kernels; only the per-sample split of the batch means differs
+    print("rel-L2 of 2-rank averaged grads: real / gp terms vs the fp32 oracle on the concatenated batch, critic total vs one process:", dict(ret))
+    for v in ret.values():
+        assert v["real"] <= 1e-2 and v["gp"] <= 1e-2, v
+        assert v["critic"] <= 1e-2, v
