@@ -3,14 +3,17 @@
 //
 // Replaces reference music_gan/audio/functions.py:97-137 (magn_phase_to_wav without the file write).
 //
-//   k_inv_magn_minmax  (m+1)/2 / bark  -> per-clip min / max                      (:111-113)
 //   k_inv_phase_accumulate  phase affine map + STRICTLY SEQUENTIAL float32 running sum along time, one thread per
 //                      (clip, bin) chain (:115-118; SURVEY B.3: a parallel or fp64 scan only reaches 44 dB on
-//                      coherent phase) -- only the dependent FADD chain is serial
-//   k_inv_polar        % 2pi, magn * (cos, sin), [f][t] -> X[t][f] frame major, fully parallel   (:120-123)
+//                      coherent phase) -- only the dependent FADD chain is serial; 128-byte row pieces are prefetched
+//                      one block ahead so a chain never waits for memory
+//   k_inv_polar        (m+1)/2 / bark (:111-112) and its per-clip min / max, % 2pi, magn * (cos, sin), [f][t] -> X[t][f]
+//                      frame major, fully parallel (:120-123).  The division by (max - min) of :113 is a per-clip
+//                      scalar and the iSTFT is linear, so it is applied to the output samples in k_istft: no separate
+//                      min / max pass over the magnitude planes
 //   k_istft            per frame: half-complex -> packed 512-pt spectrum, inverse FFT (fft512.cuh),
 //                      Hann, overlap-add of 4 frames in registers (ascending frame order), divide by the
-//                      window envelope, trim n_fft/2 at both ends                    (:125-137)
+//                      window envelope (and the magnitude range), trim n_fft/2 at both ends   (:125-137)
 #include "common.cuh"
 #include "fft512.cuh"
 #include "fft_tables.h"
@@ -32,64 +35,55 @@ __device__ __forceinline__ float magn_unscaled(float m, float gain) {
     return __fdiv_rn(__fdiv_rn(__fadd_rn(m, 1.0f), 2.0f), gain);
 }
 
-// grid (blocks, n_clips), block 256
-__global__ void __launch_bounds__(256)
-k_inv_magn_minmax(const float* __restrict__ mp, int imgs, int W, const float* __restrict__ bark, int* __restrict__ keys) {
-    __shared__ float redf[2][8];
-    const int clip = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float mn = INFINITY, mx = -INFINITY;
-    const int64_t per_img = (int64_t)kIBins * W;
-    for (int i = 0; i < imgs; ++i) {
-        const float* base = mp + (((int64_t)clip * imgs + i) * 2 + 0) * per_img;
-        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + tid; e < per_img; e += (int64_t)gridDim.x * blockDim.x) {
-            const int f = (int)(e / W);
-            const float v = magn_unscaled(base[e], bark[f]);
-            mn = fminf(mn, v); mx = fmaxf(mx, v);
-        }
-    }
-    mn = warp_min(mn); mx = warp_max(mx);
-    if (lane == 0) { redf[0][warp] = mn; redf[1][warp] = mx; }
-    __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < 8; ++w) { mn = fminf(mn, redf[0][w]); mx = fmaxf(mx, redf[1][w]); }
-        if (mn <= mx) {
-            atomicMin(&keys[clip * 4 + 0], float_key(mn));
-            atomicMax(&keys[clip * 4 + 1], float_key(mx));
-        }
-    }
-}
-
 // :115-118 -- the phase affine map and the STRICTLY SEQUENTIAL float32 running sum along time, one thread per
 // (clip, bin) chain.  Only the cheap dependent chain lives here (one FADD per step); everything per element (fmodf,
 // sincosf, magnitude) is done in parallel by k_inv_polar.  acc [n_clips][imgs][512][W] fp32 (same layout as the input).
-// grid (4, n_clips), block 128
-__global__ void __launch_bounds__(128)
+// A thread walks its row in blocks of 32 floats (one 128-byte line) and loads block k+1 before it sums block k: the
+// chain then costs its 4-cycle adds, not one memory round trip per block.
+// grid (512 / kAccThreads, n_clips), block kAccThreads
+constexpr int kAccThreads = 32;
+
+__device__ __forceinline__ float phase_affine(float v) {       // :115  ((p + 1) / 2 * 2) * pi - pi, float32 constants
+    return __fsub_rn(__fmul_rn(__fmul_rn(__fdiv_rn(__fadd_rn(v, 1.0f), 2.0f), 2.0f), kPiF), kPiF);
+}
+
+__global__ void __launch_bounds__(kAccThreads)
 k_inv_phase_accumulate(const float* __restrict__ mp, int imgs, int W, float* __restrict__ acc_out) {
-    const int clip = blockIdx.y, f = blockIdx.x * 128 + threadIdx.x;
+    const int clip = blockIdx.y, f = blockIdx.x * kAccThreads + threadIdx.x;
     float acc = 0.0f;
     bool first = true;
-    const bool vec = (W & 3) == 0;
+    const bool vec = (W & 31) == 0;
     for (int i = 0; i < imgs; ++i) {
         const float* src = mp + ((((int64_t)clip * imgs + i) * 2 + 1) * kIBins + f) * (int64_t)W;
         float* dst = acc_out + (((int64_t)clip * imgs + i) * kIBins + f) * (int64_t)W;
         int w = 0;
         if (vec) {
-            for (; w + 8 <= W; w += 8) {
-                const float4 a = __ldcs(reinterpret_cast<const float4*>(src + w)), b = __ldcs(reinterpret_cast<const float4*>(src + w + 4));
-                float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            float4 cur[8], nxt[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cur[j] = __ldcs(reinterpret_cast<const float4*>(src) + j);
+            for (; w < W; w += 32) {
+                if (w + 32 < W) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) nxt[j] = __ldcs(reinterpret_cast<const float4*>(src + w + 32) + j);
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float p = __fsub_rn(__fmul_rn(__fmul_rn(__fdiv_rn(__fadd_rn(v[j], 1.0f), 2.0f), 2.0f), kPiF), kPiF);
-                    acc = first ? p : __fadd_rn(acc, p);
-                    first = false;
-                    v[j] = acc;
+                    float v[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float p = phase_affine(v[e]);
+                        acc = first ? p : __fadd_rn(acc, p);
+                        first = false;
+                        v[e] = acc;
+                    }
+                    __stcs(reinterpret_cast<float4*>(dst + w) + j, make_float4(v[0], v[1], v[2], v[3]));
                 }
-                *reinterpret_cast<float4*>(dst + w) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(dst + w + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
             }
         }
         for (; w < W; ++w) {
-            const float p = __fsub_rn(__fmul_rn(__fmul_rn(__fdiv_rn(__fadd_rn(src[w], 1.0f), 2.0f), 2.0f), kPiF), kPiF);
+            const float p = phase_affine(src[w]);
             acc = first ? p : __fadd_rn(acc, p);
             first = false;
             dst[w] = acc;
@@ -97,18 +91,20 @@ k_inv_phase_accumulate(const float* __restrict__ mp, int imgs, int W, float* __r
     }
 }
 
-// :111-113,120-123 -- per element: magnitude de-normalisation, phase % 2pi, magn * (cos, sin); [f][t] tiles are transposed
-// through shared memory so that X[t][f] (frame major, what k_istft reads) is written in full lines.
+// :111-112,120-123 -- per element: magnitude de-normalisation (without the per-clip range, see k_istft) and its min / max,
+// phase % 2pi, magn * (cos, sin); [f][t] tiles are transposed through shared memory so that X[t][f] (frame major, what
+// k_istft reads) is written in full lines.
 // grid (ceil(Wt / 32), 16, n_clips), block 256
 __global__ void __launch_bounds__(256)
 k_inv_polar(const float* __restrict__ mp, const float* __restrict__ acc_in, int imgs, int W, const float* __restrict__ bark,
-            const int* __restrict__ keys, float2* __restrict__ X) {
+            int* __restrict__ keys, float2* __restrict__ X) {
     __shared__ float tp[32][33];
     __shared__ float tm[32][33];
+    __shared__ float redf[2][8];
     const int clip = blockIdx.z, f0 = blockIdx.y * 32;
     const int64_t Wt = (int64_t)imgs * W, tt0 = (int64_t)blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const float range = __fsub_rn(key_float(keys[clip * 4 + 1]), key_float(keys[clip * 4 + 0]));   // :113
+    float mn = INFINITY, mx = -INFINITY;
     for (int r = ty; r < 32; r += 8) {              // r = bin within the tile, tx = time within the tile
         const int64_t tt = tt0 + tx;
         float a = 0.0f, m = 0.0f;
@@ -127,8 +123,19 @@ k_inv_polar(const float* __restrict__ mp, const float* __restrict__ acc_in, int 
             const float ph = remainder_pos(tp[tx][c], kTwoPiF);                   // :120
             float sn, cs;
             sincosf(ph, &sn, &cs);
-            const float m = __fdiv_rn(magn_unscaled(tm[tx][c], gain), range);
+            const float m = magn_unscaled(tm[tx][c], gain);
+            mn = fminf(mn, m); mx = fmaxf(mx, m);
             X[((int64_t)clip * Wt + tt) * kIBins + f0 + tx] = make_float2(__fmul_rn(m, cs), __fmul_rn(m, sn));
+        }
+    }
+    mn = warp_min(mn); mx = warp_max(mx);
+    if (tx == 0) { redf[0][ty] = mn; redf[1][ty] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { mn = fminf(mn, redf[0][w]); mx = fmaxf(mx, redf[1][w]); }
+        if (mn <= mx) {
+            atomicMin(&keys[clip * 4 + 0], float_key(mn));
+            atomicMax(&keys[clip * 4 + 1], float_key(mx));
         }
     }
 }
@@ -149,7 +156,7 @@ struct IstftSmem {
 // grid (ceil(n_hops / (8*16)), n_clips), block 256
 __global__ void __launch_bounds__(kIstftWarps * 32, 2)
 k_istft(const float2* __restrict__ X, int64_t Wt, const float* __restrict__ window,
-        const DeviceTables* __restrict__ tables, float* __restrict__ wav) {
+        const DeviceTables* __restrict__ tables, const int* __restrict__ keys, float* __restrict__ wav) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     IstftSmem& s = *reinterpret_cast<IstftSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -186,6 +193,8 @@ k_istft(const float2* __restrict__ X, int64_t Wt, const float* __restrict__ wind
     float2* ex = s.ex[warp];
     const float2* Xc = X + (int64_t)clip * Wt * kIBins;
     float* out = wav + (int64_t)clip * n_hops * kIHop;
+    // :113 magn / (max - min): a per-clip scalar, applied to the output samples (the transform is linear)
+    const float range = __fsub_rn(key_float(keys[clip * 4 + 1]), key_float(keys[clip * 4 + 0]));
 
     float2 acc[16];
 #pragma unroll
@@ -239,7 +248,7 @@ k_istft(const float2* __restrict__ X, int64_t Wt, const float* __restrict__ wind
                     const int64_t tf = h + 2 - i;
                     if (tf >= 0 && tf < Wt) { e0 = __fadd_rn(e0, s.wsq[q0 + 256 * i]); e1 = __fadd_rn(e1, s.wsq[q0 + 1 + 256 * i]); }
                 }
-                float2 o = make_float2(__fdiv_rn(acc[m].x, e0), __fdiv_rn(acc[m].y, e1));
+                float2 o = make_float2(__fdiv_rn(acc[m].x, __fmul_rn(e0, range)), __fdiv_rn(acc[m].y, __fmul_rn(e1, range)));
                 __stcs(reinterpret_cast<float2*>(out + h * kIHop + q0), o);
             }
         }
@@ -284,12 +293,8 @@ int mg_istft_from_magif_f32(const float* magn_phase, int n_clips, int imgs_per_c
     if (e != cudaSuccess) { set_last_cuda_error("tables", e); return MG_ERR_LAUNCH; }
     cudaStream_t st = (cudaStream_t)stream;
     launch_init_keys(w.keys, n_clips, st);
-    const int64_t per_img = (int64_t)kIBins * width;
-    const unsigned gx = (unsigned)max((int64_t)1, min((int64_t)592, per_img / 1024));
-    { ProfScope ps("k_inv_magn_minmax", st);
-      k_inv_magn_minmax<<<dim3(gx, n_clips), 256, 0, st>>>(magn_phase, imgs_per_clip, width, bark_gain, w.keys); }
     { ProfScope ps("k_inv_phase_accumulate", st);
-      k_inv_phase_accumulate<<<dim3(4, n_clips), 128, 0, st>>>(magn_phase, imgs_per_clip, width, w.acc); }
+      k_inv_phase_accumulate<<<dim3(kIBins / kAccThreads, n_clips), kAccThreads, 0, st>>>(magn_phase, imgs_per_clip, width, w.acc); }
     { ProfScope ps("k_inv_polar", st);
       k_inv_polar<<<dim3((unsigned)((Wt + 31) / 32), 16, n_clips), 256, 0, st>>>(magn_phase, w.acc, imgs_per_clip, width, bark_gain, w.keys, w.X); }
     const int64_t n_hops = Wt - 1;
@@ -297,7 +302,7 @@ int mg_istft_from_magif_f32(const float* magn_phase, int n_clips, int imgs_per_c
     static bool attr_done = false;
     if (!attr_done) { cudaFuncSetAttribute(k_istft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IstftSmem)); attr_done = true; }
     { ProfScope ps("k_istft", st);
-      k_istft<<<dim3(gh, n_clips), kIstftWarps * 32, sizeof(IstftSmem), st>>>(w.X, Wt, window, device_tables_ptr(), wav); }
+      k_istft<<<dim3(gh, n_clips), kIstftWarps * 32, sizeof(IstftSmem), st>>>(w.X, Wt, window, device_tables_ptr(), w.keys, wav); }
     return check_launch("istft");
 }
 

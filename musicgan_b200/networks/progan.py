@@ -30,6 +30,10 @@ def _blend(old: th.Tensor, new: th.Tensor, alpha) -> th.Tensor:
     `alpha` is the reference's Python float or a 0-dim device tensor (graphed.py feeds it to captured graphs that way)."""
     if th.is_tensor(alpha):
         alpha = alpha.to(dtype=old.dtype)
+    elif old.dtype == th.bfloat16:
+        # a tensor weight of a bf16 blend is itself bf16: round the float the same way, so that the eager steps and the
+        # captured graphs (alpha on the device) compute the same blend (2^-9 relative on alpha, below the rounding of the result)
+        alpha = float(th.tensor(float(alpha)).bfloat16())
     return th.lerp(old, new.to(old.dtype), alpha)
 
 
