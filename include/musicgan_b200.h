@@ -138,10 +138,12 @@ int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* 
  * K step: ~16 significand bits): the precise path of the layers whose output height is <= 32, where bf16 operand
  * rounding flips LeakyReLU masks and moves the WGAN-GP gradients by several percent (conv_split.cu).
  * x [B][H(/2)][W(/2)][Cin] fp32, y [B][H][W][Cout] fp32, y_bf16 optional bf16 copy of y (operand of
- * mg_conv3x3_wgrad_bf16), `packed` from mg_conv3x3_split_pack_weights (>= mg_conv3x3_split_workspace_bytes; dgrad != 0
- * packs the data-gradient orientation, to be used with flag 8).  flags 1, 2, 4, 8 as mg_conv3x3_bf16. */
+ * mg_conv3x3_wgrad_bf16), `packed` from mg_conv3x3_split_pack_weights (>= mg_conv3x3_split_workspace_bytes; mode bit 0
+ * packs the data-gradient orientation, to be used with flag 8; mode bit 1 packs w = hi + mid + lo, the fp32 weight
+ * exactly, to be used with flag 32: five MMAs per K step -- the critic's forward convolutions, where one flipped
+ * LeakyReLU mask in a 2 x 2-pixel layer moves the penalty gradient by percents).  flags 1, 2, 4, 8 as mg_conv3x3_bf16. */
 size_t mg_conv3x3_split_workspace_bytes(int Cin, int Cout);
-int mg_conv3x3_split_pack_weights(const float* w_f32, int Cin, int Cout, int dgrad, void* packed, size_t packed_bytes, mgStream stream);
+int mg_conv3x3_split_pack_weights(const float* w_f32, int Cin, int Cout, int mode, void* packed, size_t packed_bytes, mgStream stream);
 int mg_conv3x3_split_f32(const float* x, const void* packed, const float* bias, float* y, void* y_bf16, float* inv_norm,
                          int B, int H, int W, int Cin, int Cout, int flags, mgStream stream);
 
@@ -210,19 +212,6 @@ int mg_unpool2_lrelu_bwd_bf16(const void* gp, const void* h, void* gz, float* gb
  * NULL; needs ws of mg_colsum_workspace_bytes(C)). */
 int mg_pixelnorm_lrelu_bwd_bf16(const void* go, const void* o, const float* inv_norm, void* gz, float* gb, void* ws, size_t ws_bytes,
                                 int64_t n_pixels, int C, mgStream stream);
-
-/* ------------------------------------------------------------------------------------------
- * Test-only probe of the tcgen05 / TMEM conventions the convolution kernels rely on (one tile).
- * mode 0: A [Ra][K], B [N][K] bf16 (K contiguous);  D[m][n] = sum_k A[row_off + (m/8)*grp_rows + m%8][k] * B[n][k]
- * mode 1: A [K][128], B [K][N] bf16 (M / N contiguous);  D[m][n] = sum_k A[k][m] * B[k][n]
- * D [128][N] fp32.
- * ---------------------------------------------------------------------------------------- */
-int mg_debug_umma_gemm(const void* A, const void* B, float* D, int K, int N, int mode, int Ra, int row_off,
-                       int grp_rows, mgStream stream);
-/* Test-only probe of the tcgen05.st shapes used by the weight-gradient kernel's operand staging: one store of
- * shape 0: 16x64b.x1, 1: 16x128b.x1, 2: 16x128b.x2, 3: 16x256b.x1 by warp 0 with register values
- * 0x1000 | thread << 4 | (register index + 1); out [128 lanes][32 columns] uint32 = the TMEM block afterwards. */
-int mg_debug_tmem_store(uint32_t* out, int shape, int lane_off, int col_off, mgStream stream);
 
 /* The same memory-bound layers on fp32 NHWC activations (precise path of the low-resolution layers; same arguments,
  * every `void*` activation / mask tensor is fp32 instead of bf16). */

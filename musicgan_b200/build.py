@@ -17,6 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmusicgan_b200.so")
+DEBUG_LIB = os.path.join(HERE, "libmusicgan_b200_debug.so")      # test-only probes (debug_*.cu), never loaded by the product
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -61,16 +62,21 @@ def build(force: bool = False, verbose: bool = True) -> str:
     hdr = _headers_digest()
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(lambda s: _compile_one(s, hdr, force), srcs))
-    newest = max(os.path.getmtime(o) for o in objs)
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
-        cmd = [NVCC, *ARCH_FLAGS, "-shared", "-o", LIB, *objs]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-        if verbose:
-            print(f"[musicgan_b200.build] linked {LIB} from {len(objs)} objects")
-    elif verbose:
-        print(f"[musicgan_b200.build] {LIB} up to date")
+    is_debug = lambda o: os.path.basename(o).startswith("debug_")
+    product = [o for o in objs if not is_debug(o)]
+    # the probes need the library's error / profiling helpers: lib.o is linked into both
+    debug = [o for o in objs if is_debug(o) or os.path.basename(o) == "lib.o"]
+    for lib, members in ((LIB, product), (DEBUG_LIB, debug)):
+        newest = max(os.path.getmtime(o) for o in members)
+        if force or not os.path.exists(lib) or os.path.getmtime(lib) < newest:
+            cmd = [NVCC, *ARCH_FLAGS, "-shared", "-o", lib, *members]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+            if verbose:
+                print(f"[musicgan_b200.build] linked {lib} from {len(members)} objects")
+        elif verbose:
+            print(f"[musicgan_b200.build] {lib} up to date")
     return LIB
 
 

@@ -36,17 +36,24 @@ constexpr int kSeg = 64;          // frames per unwrap segment
 
 __device__ DeviceTables g_tables;
 
-static std::once_flag g_tables_once;
-static cudaError_t g_tables_status = cudaSuccess;
+// __device__ symbols exist once PER DEVICE: the tables are uploaded the first time each device is used (a process may
+// drive several GPUs through the Python API's device= arguments)
+constexpr int kMaxDevices = 64;
+static std::once_flag g_tables_once[kMaxDevices];
+static cudaError_t g_tables_status[kMaxDevices];
 cudaError_t ensure_tables() {
-    std::call_once(g_tables_once, [] {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    std::call_once(g_tables_once[dev], [dev] {
         DeviceTables* h = new DeviceTables;
         build_fft_tables(&h->fft);
         build_split_twiddles(h->w1024);
-        g_tables_status = cudaMemcpyToSymbol(g_tables, h, sizeof(DeviceTables));
+        g_tables_status[dev] = cudaMemcpyToSymbol(g_tables, h, sizeof(DeviceTables));
         delete h;
     });
-    return g_tables_status;
+    return g_tables_status[dev];
 }
 const DeviceTables* device_tables_ptr() {
     void* p = nullptr;
@@ -448,13 +455,11 @@ static int launch_stft(int mode, const float* wav, int64_t n_samples, int channe
     const size_t smem = sizeof(StftSmem);
     ProfScope ps("k_stft", st);
     if (mode == STFT_POLAR) {
-        static bool attr_done = false;
-        if (!attr_done) { cudaFuncSetAttribute(k_stft<STFT_POLAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
+        cudaFuncSetAttribute(k_stft<STFT_POLAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      // per device: set on every call
         k_stft<STFT_POLAR><<<grid, kStftWarps * 32, smem, st>>>(wav, n_samples, channels, clip_stride, n_frames, window, bark,
                                                                 device_tables_ptr(), out_a, out_b, keys);
     } else {
-        static bool attr_done = false;
-        if (!attr_done) { cudaFuncSetAttribute(k_stft<STFT_COMPLEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
+        cudaFuncSetAttribute(k_stft<STFT_COMPLEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_stft<STFT_COMPLEX><<<grid, kStftWarps * 32, smem, st>>>(wav, n_samples, channels, clip_stride, n_frames, window, bark,
                                                                   device_tables_ptr(), out_a, out_b, keys);
     }

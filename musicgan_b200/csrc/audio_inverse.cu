@@ -299,8 +299,7 @@ int mg_istft_from_magif_f32(const float* magn_phase, int n_clips, int imgs_per_c
       k_inv_polar<<<dim3((unsigned)((Wt + 31) / 32), 16, n_clips), 256, 0, st>>>(magn_phase, w.acc, imgs_per_clip, width, bark_gain, w.keys, w.X); }
     const int64_t n_hops = Wt - 1;
     const unsigned gh = (unsigned)((n_hops + kIstftWarps * kHopsPerWarp - 1) / (kIstftWarps * kHopsPerWarp));
-    static bool attr_done = false;
-    if (!attr_done) { cudaFuncSetAttribute(k_istft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IstftSmem)); attr_done = true; }
+    cudaFuncSetAttribute(k_istft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IstftSmem));      // per device
     { ProfScope ps("k_istft", st);
       k_istft<<<dim3(gh, n_clips), kIstftWarps * 32, sizeof(IstftSmem), st>>>(w.X, Wt, window, device_tables_ptr(), w.keys, wav); }
     return check_launch("istft");

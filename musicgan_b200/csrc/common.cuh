@@ -31,6 +31,19 @@ struct ProfScope {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// SM count of the CURRENT device (cached per device: the Python API accepts any device)
+inline int current_sm_count() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cache[dev]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cache[dev] = n > 0 ? n : 148;
+    }
+    return cache[dev];
+}
+
 // ---- programmatic dependent launch ------------------------------------------------------------------------------
 // A training step is ~1000 short dependent kernels.  Launched with programmaticStreamSerialization the next kernel's
 // CTAs may become resident and run their on-chip prologue (barrier init, TMEM allocation, index tables) while the

@@ -21,10 +21,11 @@ inline FastDiv make_fast_div(int d) { FastDiv f; f.m = ((1ull << 40) / (unsigned
 __device__ __forceinline__ int fast_div(int n, FastDiv f) { return (int)(((unsigned long long)(unsigned)n * f.m) >> 40); }
 
 // Weight packing of the split-operand kernel (conv_split.cu):
-// fp32 [Cout][Cin][3][3] -> split bf16 [K/16][tap][hi, lo][2 chunks][N][8]   (N, K = GEMM channel counts)
+// fp32 [Cout][Cin][3][3] -> split bf16 [K/16][tap][part][2 chunks][N][8]   (N, K = GEMM channel counts); `wparts` = 2:
+// w = hi + lo (16 significand bits), 3: w = hi + mid + lo (24 bits, the fp32 weight exactly)
 //   transpose_flip = 0: B[n = co][k = ci] of tap (ky,kx) = w[co][ci][ky][kx]
 //   transpose_flip = 1: data gradient, B[n = ci][k = co] = w[co][ci][2-ky][2-kx]
-__device__ __forceinline__ void pack_weights_split_range(const float* __restrict__ w, int Cout, int Cin, int transpose_flip,
+__device__ __forceinline__ void pack_weights_split_range(const float* __restrict__ w, int Cout, int Cin, int transpose_flip, int wparts,
                                                          __nv_bfloat16* __restrict__ out, int first, int stride) {
     const int N = transpose_flip ? Cin : Cout, K = transpose_flip ? Cout : Cin;
     const int total = 9 * N * K;                       // (hi, lo) pairs
@@ -38,11 +39,14 @@ __device__ __forceinline__ void pack_weights_split_range(const float* __restrict
         const int ky = tap / 3, kx = tap % 3;
         const float v = transpose_flip ? w[(((size_t)k * Cin + n) * 3 + (2 - ky)) * 3 + (2 - kx)]
                                        : w[(((size_t)n * Cin + k) * 3 + ky) * 3 + kx];
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const float r1 = v - __bfloat162float(hi);
+        const __nv_bfloat16 mid = __float2bfloat16_rn(r1), lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
         // destination: [cg][tap][part][chunk][n][e]
-        const size_t base = ((size_t)(cg * 9 + tap) * 2) * 2 * N * 8;
+        const size_t base = ((size_t)(cg * 9 + tap) * wparts) * 2 * N * 8;
         out[base + ((size_t)(0 * 2 + chunk) * N + n) * 8 + e] = hi;
-        out[base + ((size_t)(1 * 2 + chunk) * N + n) * 8 + e] = lo;
+        out[base + ((size_t)(1 * 2 + chunk) * N + n) * 8 + e] = mid;
+        if (wparts == 3) out[base + ((size_t)(2 * 2 + chunk) * N + n) * 8 + e] = lo;
     }
 }
 #endif

@@ -409,7 +409,7 @@ k_pack_weights_multi(const mgPackJob* __restrict__ jobs) {
     const mgPackJob j = jobs[blockIdx.y];
     const int first = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     if (j.kind == 0) pack_weights_range(j.w, j.cout_fwd, j.cin_fwd, j.flip, j.nt, j.parts, (__nv_bfloat16*)j.out, first, stride);
-    else pack_weights_split_range(j.w, j.cout_fwd, j.cin_fwd, j.flip, (__nv_bfloat16*)j.out, first, stride);
+    else pack_weights_split_range(j.w, j.cout_fwd, j.cin_fwd, j.flip, j.parts, (__nv_bfloat16*)j.out, first, stride);
 }
 
 struct ConvPlan { int Nt, stages, tmem_cols, n_slices, occupancy, epi_warps, n_acc, acc_stride, mb, blk_stride, halo_pos, halo_pitch; size_t smem; };
@@ -502,7 +502,7 @@ int mg_pack_job_fill(mgPackJob* job, const float* w_f32, void* packed, int Cin, 
     const int dgrad = mode & 1;
     job->w = w_f32; job->out = packed; job->kind = kind ? 1 : 0; job->flip = dgrad;
     job->cout_fwd = dgrad ? Cin : Cout; job->cin_fwd = dgrad ? Cout : Cin;
-    job->parts = (!kind && (mode & 2)) ? 2 : 1;
+    job->parts = kind ? ((mode & 2) ? 3 : 2) : ((mode & 2) ? 2 : 1);
     job->nt = 0;
     if (!kind) {
         ConvPlan pl = plan_conv(Cin, Cout, (mode & 4) != 0, 0, job->parts);
@@ -568,8 +568,7 @@ int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* 
     p.div_img = make_fast_div(p.tiles_per_img);
     p.div_tx = make_fast_div(p.tiles_x);
     if (p.n_tiles >= (1 << 20)) return MG_ERR_UNSUPPORTED;
-    static int sm_count = 0;
-    if (!sm_count) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+    const int sm_count = current_sm_count();
     p.slope = (flags & 1) ? 0.2f : 1.0f;
     const bool ba = bias != nullptr || (flags & 1);
     const bool o4 = pl.occupancy == 4;

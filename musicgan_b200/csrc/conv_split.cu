@@ -7,7 +7,10 @@
 // (2^-9) move the WGAN-GP gradients by 2..10 % (scripts/precision_study.py).  Here every operand is the sum of two
 // bf16 numbers, x = hi + lo (16 significand bits), and the product is accumulated in fp32 as
 //       hi_x * hi_w  +  lo_x * hi_w  +  hi_x * lo_w                       (three tcgen05.mma per K step)
-// which puts the pre-activation error near 2^-16: the masks agree with the fp32 reference's.
+// which puts the pre-activation error near 2^-16: the masks agree with the fp32 reference's.  The critic's forward
+// convolutions go one step further (flag 32): w = hi + mid + lo carries the fp32 weight exactly and two more products
+// (lo_x * mid_w, hi_x * lo_w) are added -- with 1e5 pre-activations per step a few sit within 1e-5 of zero, and one
+// flipped mask in a 2 x 2-pixel layer moves the gradient-penalty gradient by percents (golden case stage2_b3).
 //
 // Structure (small layers: simplicity over the last cycle):
 //   * one CTA = one 16 x 8 pixel tile of one image (GEMM M = 128) x one slice of output channels;
@@ -33,7 +36,8 @@ constexpr int kSplitAPlane = 2 * kHaloPitch * 16; // bytes of one (hi or lo) pla
 
 struct SplitParams {
     const float* x;              // [B][Hin][Win][Cin] fp32
-    const uint4* wpack;          // [Cin/16][9 taps][hi, lo][2 chunks][Cout][8 bf16]
+    const uint4* wpack;          // [Cin/16][9 taps][wparts][2 chunks][Cout][8 bf16]
+    int wparts;                  // 2: w = hi + lo; 3: w = hi + mid + lo
     const float* bias;           // [Cout] or null
     float* y;                    // [B][H][W][Cout] fp32
     __nv_bfloat16* y16;          // optional bf16 copy of y (operand of the bf16 weight-gradient kernel), or null
@@ -116,13 +120,14 @@ k_conv3x3_split(const SplitParams p) {
                 }
             }
         }
-        const int w_items = 36 * nt;                 // 16-byte chunks of packed weights per channel group (this slice)
+        const int w_rows = 18 * p.wparts;            // [tap][part][chunk] rows of packed weights per channel group
+        const int w_items = w_rows * nt;             // 16-byte chunks of them in this slice
         int slot = 0; uint32_t ph = 0;
         for (int cg = 0; cg < n_cg; ++cg) {
             mbar_wait(&empty[slot], ph ^ 1u);
             unsigned char* st = smem + (size_t)slot * p.stage_bytes;
             // weights: [tap][part][chunk] rows of Cout entries; this slice takes nt of them starting at n0
-            const uint4* wsrc = p.wpack + (size_t)cg * 36 * p.Cout + n0;
+            const uint4* wsrc = p.wpack + (size_t)cg * w_rows * p.Cout + n0;
             const uint32_t sB = smem_u32(st + 2 * kSplitAPlane);
             for (int i = pt; i < w_items; i += 128) {
                 const int q = i / nt, n = i - q * nt;
@@ -165,15 +170,19 @@ k_conv3x3_split(const SplitParams p) {
                 const uint64_t a_hi = smem_desc(sA, (uint32_t)kHaloPitch * 16u, kHaloW * 16u);
                 const uint64_t a_lo = smem_desc(sA + kSplitAPlane, (uint32_t)kHaloPitch * 16u, kHaloW * 16u);
                 const uint64_t b0 = smem_desc(sA + 2 * kSplitAPlane, (uint32_t)nt * 16u, 128u);
-                const uint32_t b_part = (uint32_t)(2 * nt);          // 16-byte units between hi and lo weights of a tap
+                const uint32_t b_part = (uint32_t)(2 * nt);          // 16-byte units between the parts of a tap's weights
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     const uint64_t off = (uint64_t)((tap / 3) * kHaloW + (tap % 3));
-                    const uint64_t b_hi = b0 + (uint64_t)(tap * 2) * b_part, b_lo = b_hi + b_part;
+                    const uint64_t b_hi = b0 + (uint64_t)(tap * p.wparts) * b_part, b_mid = b_hi + b_part;
                     mma_bf16(tmem_base, a_hi + off, b_hi, idesc, accum);
                     accum = 1;
                     mma_bf16(tmem_base, a_lo + off, b_hi, idesc, 1u);
-                    mma_bf16(tmem_base, a_hi + off, b_lo, idesc, 1u);
+                    mma_bf16(tmem_base, a_hi + off, b_mid, idesc, 1u);
+                    if (p.wparts == 3) {
+                        mma_bf16(tmem_base, a_lo + off, b_mid, idesc, 1u);
+                        mma_bf16(tmem_base, a_hi + off, b_mid + b_part, idesc, 1u);
+                    }
                 }
                 mma_commit(&empty[slot]);
                 if (cg + 1 == n_cg) mma_commit(acc_full);
@@ -243,16 +252,16 @@ k_conv3x3_split(const SplitParams p) {
     if (warp == 8) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-__global__ void k_pack_weights_split(const float* __restrict__ w, int Cout, int Cin, int transpose_flip,
+__global__ void k_pack_weights_split(const float* __restrict__ w, int Cout, int Cin, int transpose_flip, int wparts,
                                      __nv_bfloat16* __restrict__ out) {
     pdl_trigger();
     pdl_wait();
-    pack_weights_split_range(w, Cout, Cin, transpose_flip, out, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    pack_weights_split_range(w, Cout, Cin, transpose_flip, wparts, out, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 struct SplitPlan { int Nt, n_slices, stages, tmem_cols; unsigned stage_bytes; size_t smem; };
 
-static SplitPlan plan_split(int Cin, int Cout, bool full_n, int n_tiles) {
+static SplitPlan plan_split(int Cin, int Cout, bool full_n, int n_tiles, int wparts) {
     SplitPlan pl{};
     const size_t budget = 216 * 1024;
     int slices = full_n ? 1 : (Cout + 79) / 80;
@@ -261,7 +270,7 @@ static SplitPlan plan_split(int Cin, int Cout, bool full_n, int n_tiles) {
     int Nt = ((Cout / 16 + slices - 1) / slices) * 16;
     for (;; Nt -= 16) {
         if (Nt < 16) return pl;
-        const unsigned stage = (unsigned)align_up((size_t)2 * kSplitAPlane + (size_t)576 * Nt, 128);
+        const unsigned stage = (unsigned)align_up((size_t)2 * kSplitAPlane + (size_t)288 * wparts * Nt, 128);
         int stages = (int)((budget - 256) / stage);
         if (stages < 2) { if (full_n) { if (stages < 1) return pl; } else continue; }
         if (stages > kSplitStagesMax) stages = kSplitStagesMax;
@@ -282,23 +291,26 @@ using namespace mg;
 extern "C" {
 
 size_t mg_conv3x3_split_workspace_bytes(int Cin, int Cout) {
-    return align_up((size_t)9 * Cin * Cout * 4, 256);
+    return align_up((size_t)9 * Cin * Cout * 6, 256);       // room for three parts
 }
 
-int mg_conv3x3_split_pack_weights(const float* w_f32, int Cin, int Cout, int dgrad, void* packed, size_t packed_bytes, mgStream stream) {
+// mode: bit 0 data-gradient orientation, bit 1 three parts (hi + mid + lo, for mg_conv3x3_split_f32 with flag 32)
+int mg_conv3x3_split_pack_weights(const float* w_f32, int Cin, int Cout, int mode, void* packed, size_t packed_bytes, mgStream stream) {
     if (!w_f32 || !packed) return MG_ERR_BAD_ARG;
     if (Cin < 16 || Cout < 16 || (Cin & 15) || (Cout & 15) || Cin > 256 || Cout > 256) return MG_ERR_UNSUPPORTED;
-    if (packed_bytes < (size_t)9 * Cin * Cout * 4) return MG_ERR_WORKSPACE;
+    const int dgrad = mode & 1, wparts = (mode & 2) ? 3 : 2;
+    if (packed_bytes < (size_t)9 * Cin * Cout * 2 * wparts) return MG_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope ps("k_pack_weights_split", st);
     // Cin, Cout are those of the GEMM (for dgrad: Cin = channels of dY = forward Cout)
     const int fwd_cout = dgrad ? Cin : Cout, fwd_cin = dgrad ? Cout : Cin;
     const int total = 9 * Cin * Cout;
-    launch_pdl(k_pack_weights_split, dim3((total + 255) / 256), dim3(256), 0, st, w_f32, fwd_cout, fwd_cin, dgrad ? 1 : 0, (__nv_bfloat16*)packed);
+    launch_pdl(k_pack_weights_split, dim3((total + 255) / 256), dim3(256), 0, st, w_f32, fwd_cout, fwd_cin, dgrad ? 1 : 0, wparts, (__nv_bfloat16*)packed);
     return check_launch("k_pack_weights_split");
 }
 
-// flags as mg_conv3x3_bf16: 1 LeakyReLU(0.2), 2 PixelNorm, 4 nearest x2 upsampled input, 8 data gradient
+// flags as mg_conv3x3_bf16: 1 LeakyReLU(0.2), 2 PixelNorm, 4 nearest x2 upsampled input, 8 data gradient; 32: `packed` holds
+// three weight parts (mode bit 1 of the pack call)
 int mg_conv3x3_split_f32(const float* x, const void* packed, const float* bias, float* y, void* y_bf16, float* inv_norm,
                          int B, int H, int W, int Cin, int Cout, int flags, mgStream stream) {
     if (!x || !y || !packed) return MG_ERR_BAD_ARG;
@@ -309,12 +321,13 @@ int mg_conv3x3_split_f32(const float* x, const void* packed, const float* bias, 
     p.tiles_x = (W + kTileW - 1) / kTileW; p.tiles_y = (H + kTileH - 1) / kTileH;
     const long long n_tiles = (long long)B * p.tiles_x * p.tiles_y;
     if (n_tiles >= (1ll << 30)) return MG_ERR_UNSUPPORTED;
-    SplitPlan pl = plan_split(Cin, Cout, pn, (int)n_tiles);
+    const int wparts = (flags & 32) ? 3 : 2;
+    SplitPlan pl = plan_split(Cin, Cout, pn, (int)n_tiles, wparts);
     if (pl.Nt == 0 || (pn && pl.n_slices != 1)) return MG_ERR_UNSUPPORTED;
     p.x = x; p.wpack = (const uint4*)packed; p.bias = bias; p.y = y; p.y16 = (__nv_bfloat16*)y_bf16; p.inv_norm = inv_norm;
     p.B = B; p.H = H; p.W = W; p.Hin = ups ? H / 2 : H; p.Win = ups ? W / 2 : W; p.Cin = Cin; p.Cout = Cout;
     p.upsample = ups; p.lrelu = flags & 1; p.pixelnorm = pn;
-    p.Nt = pl.Nt; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols; p.stage_bytes = pl.stage_bytes;
+    p.Nt = pl.Nt; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols; p.stage_bytes = pl.stage_bytes; p.wparts = wparts;
     const bool ba = bias != nullptr || (flags & 1);
     auto kern = pn ? (ba ? k_conv3x3_split<true, true> : k_conv3x3_split<true, false>)
                    : (ba ? k_conv3x3_split<false, true> : k_conv3x3_split<false, false>);

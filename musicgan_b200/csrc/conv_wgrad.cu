@@ -337,9 +337,7 @@ k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dw, int Cin, 
 using namespace mg;
 
 static void wgrad_grid(int n_tiles, int Cin, int Cout, int* nb_out, int* groups_out, int* gx_out) {
-    static int sm_count = 0;
-    if (!sm_count) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
-    if (sm_count <= 0) sm_count = 148;
+    const int sm_count = current_sm_count();
     const int n_blocks = (9 * Cin + 127) / 128;
     int nb = 512 / (Cout + 128); nb = nb > kMaxBlocks ? kMaxBlocks : (nb < 1 ? 1 : nb);
     nb = nb > n_blocks ? n_blocks : nb;
@@ -401,8 +399,6 @@ extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, v
     p.div_img = make_fast_div(p.tiles_per_img);
     p.div_tx = make_fast_div(p.tiles_x);
     if (p.n_tiles >= (1 << 20)) return MG_ERR_UNSUPPORTED;
-    static int sm_count = 0;
-    if (!sm_count) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
     cudaFuncSetAttribute(k_conv3x3_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaStream_t st = (cudaStream_t)stream;
     {

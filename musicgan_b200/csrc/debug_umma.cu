@@ -2,6 +2,7 @@
 // no-swizzle staging, row-offset starts, MN-major operands, TMEM lane mapping).  One CTA, one tile.
 // Not on any product path; called only by tests/test_umma_probe_gpu.py.
 #include "common.cuh"
+#include "../../include/musicgan_b200_debug.h"
 #include "umma.cuh"
 
 namespace mg {

@@ -148,6 +148,11 @@ class GraphedSteps:
                 self._generator_body()
         th.cuda.current_stream().wait_stream(side)
         th.cuda.synchronize()
+        # the job tables of the one-launch weight packing are uploaded here, outside the capture (a host-to-device copy
+        # of pageable memory cannot be captured); inside the graphs prepack() only launches the kernel
+        ops.prepack(self.disc)
+        ops.prepack(self.gen)
+        th.cuda.synchronize()
         ops.invalidate_pack_cache()
         self._gd = th.cuda.CUDAGraph()
         with th.cuda.graph(self._gd):

@@ -114,7 +114,7 @@ class ConvBiasLReLU(Function):
 
     @staticmethod
     def forward(ctx, x, w, b):
-        y = ops.conv3x3(_act(x), w.float().contiguous(), b.float().contiguous(), lrelu=True, split_w=True)
+        y = ops.conv3x3(_act(x), w.float().contiguous(), b.float().contiguous(), lrelu=True, split_w=True, exact_w=True)
         ctx.save_for_backward(x, w, y)
         return y
 
@@ -185,7 +185,7 @@ class ConvBiasLReLUPool(Function):
 
     @staticmethod
     def forward(ctx, x, w, b):
-        h = ops.conv3x3(_act(x), w.float().contiguous(), b.float().contiguous(), lrelu=True, split_w=True)
+        h = ops.conv3x3(_act(x), w.float().contiguous(), b.float().contiguous(), lrelu=True, split_w=True, exact_w=True)
         ctx.save_for_backward(x, w, h)
         return ops.pool2(h)
 

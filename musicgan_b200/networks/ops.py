@@ -13,12 +13,13 @@ import torch as th
 
 from .. import _lib
 
-FLAG_LRELU, FLAG_PIXELNORM, FLAG_UPSAMPLE_IN, FLAG_DGRAD, FLAG_SPLIT_W = 1, 2, 4, 8, 16
+FLAG_LRELU, FLAG_PIXELNORM, FLAG_UPSAMPLE_IN, FLAG_DGRAD, FLAG_SPLIT_W, FLAG_W3 = 1, 2, 4, 8, 16, 32
 
 # Layers whose OUTPUT height is <= PRECISE_MAX_RES run on fp32 activations with split-bf16 operands (conv_split.cu): on
 # those few-pixel layers bf16 operand rounding flips LeakyReLU masks and moves the WGAN-GP gradients by 2-10 %
-# (scripts/precision_study.py; north_star asks for 1e-2).  0 switches the precise path off.
-PRECISE_MAX_RES = int(os.environ.get("MG_PRECISE_MAX_RES", "32"))
+# (scripts/precision_study.py; north_star asks for 1e-2).  With 32 the batch-1 golden cases at stages 6 / 7 sit at
+# 1.0-1.1e-2, with 64 at 7-8e-3 (emulated and measured).  0 switches the precise path off.
+PRECISE_MAX_RES = int(os.environ.get("MG_PRECISE_MAX_RES", "64"))
 # Forward convolutions of the bf16 layers take their weights as hi + lo bf16 pairs (flag 16); 0 = plain bf16 weights.
 SPLIT_W = os.environ.get("MG_SPLIT_W", "1") != "0"
 
@@ -205,10 +206,11 @@ def _sfx(x: th.Tensor) -> str:
 
 
 def conv3x3(x: th.Tensor, w: th.Tensor, bias=None, *, lrelu=False, pixelnorm=False, upsample_in=False,
-            dgrad=False, want_inv_norm=False, split_w=False):
+            dgrad=False, want_inv_norm=False, split_w=False, exact_w=False):
     """y = conv3x3(x) (+bias) (+LeakyReLU 0.2) (+PixelNorm); `upsample_in` reads x through a nearest x2
     upsampling; `dgrad` computes the data gradient of the forward conv with weight `w` for x = dL/dy.
-    fp32 x -> the split-operand kernel (fp32 y); bf16 x -> the bf16 kernel (bf16 y), with hi + lo weights if `split_w`."""
+    fp32 x -> the split-operand kernel (fp32 y; `exact_w`: three weight parts = the fp32 weight exactly, the critic's
+    forward convolutions); bf16 x -> the bf16 kernel (bf16 y), with hi + lo weights if `split_w`."""
     _check_act(x, "conv3x3 x")
     assert w.is_cuda and w.dtype == th.float32 and w.is_contiguous() and w.dim() == 4 and w.shape[2:] == (3, 3)
     B, C, Hin, Win = x.shape
@@ -230,7 +232,9 @@ def conv3x3(x: th.Tensor, w: th.Tensor, bias=None, *, lrelu=False, pixelnorm=Fal
         assert bias.dtype == th.float32 and bias.numel() == cout and bias.is_cuda
     _account(2.0 * B * H * W * 9 * cin * cout, float(x.element_size()) * (x.numel() + y.numel()))
     if precise:
-        kind = ("split", 1 if dgrad else 0)
+        if exact_w and not pixelnorm:
+            flags |= FLAG_W3
+        kind = ("split", (1 if dgrad else 0) | (2 if flags & FLAG_W3 else 0))
         packed = _packed_weights(w, cin, cout, kind)
         with th.cuda.device(x.device):
             if packed is None:

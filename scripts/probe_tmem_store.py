@@ -2,8 +2,8 @@
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch as th
-from musicgan_b200 import _lib
-l = _lib.lib()
+from musicgan_b200 import build
+l = ctypes.CDLL(build.DEBUG_LIB)
 l.mg_debug_tmem_store.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
 for shape, lane_off, col_off in [(0, 0, 0), (1, 0, 0), (2, 0, 0), (3, 0, 0), (1, 16, 4), (2, 16, 8)]:
     out = th.zeros(128, 32, dtype=th.int32, device="cuda")

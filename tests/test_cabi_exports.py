@@ -7,26 +7,27 @@ import re
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared():
-    names = set()
-    for fn in sorted(os.listdir(os.path.join(ROOT, "include"))):
-        if not fn.endswith(".h"):
-            continue
-        src = open(os.path.join(ROOT, "include", fn)).read()
-        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-        names |= set(re.findall(r"\b(mg_[a-z0-9_]+)\s*\(", src))
-    return sorted(names)
+def _declared(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mg_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():
     from musicgan_b200 import build, _lib
     build.build(verbose=False)
     l = ctypes.CDLL(_lib.LIB_PATH)
-    declared = _declared()
-    assert len(declared) >= 10
+    declared = _declared("musicgan_b200.h")
+    assert len(declared) >= 30
     missing = [n for n in declared if not hasattr(l, n)]
     assert not missing, missing
     assert l.mg_version() >= 100
+    # the test-only probes live in their own library, not in the product
+    dbg = ctypes.CDLL(build.DEBUG_LIB)
+    probes = _declared("musicgan_b200_debug.h")
+    assert probes and all(hasattr(dbg, n) for n in probes)
+    assert not any(hasattr(l, n) for n in probes)
+    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["musicgan_b200.h", "musicgan_b200_debug.h"]
 
 
 def test_host_only_entry_points():

@@ -267,6 +267,29 @@ def test_split_fprop_and_dgrad(B, Cin, Cout, H, W):
     assert dx.shape == (B, Cin, H, W) and e <= 2e-5, e
 
 
+def test_split_exact_weights():
+    """flag 32: w = hi + mid + lo (the fp32 weight exactly, five MMAs per K step).  On a constant image a centre tap of
+    1 + 2^-9 + 2^-19 and a left tap of -1 leave 2^-9 + 2^-19 in the interior; two parts (hi + mid) stop at 2^-9."""
+    from musicgan_b200.networks import ops
+    for C in (16, 96, 160):
+        x = torch.ones(2, C, 8, 16, device="cuda").contiguous(memory_format=torch.channels_last)
+        w = torch.zeros(C, C, 3, 3, device="cuda")
+        w[torch.arange(C), torch.arange(C), 1, 1] = 1.0 + 2.0 ** -9 + 2.0 ** -19
+        w[torch.arange(C), torch.arange(C), 1, 0] = -1.0
+        y3 = ops.conv3x3(x, w, None, exact_w=True)
+        y2 = ops.conv3x3(x, w, None)
+        assert torch.equal(y3[:, :, :, 1:], torch.full_like(y3[:, :, :, 1:], 2.0 ** -9 + 2.0 ** -19))
+        assert torch.equal(y2[:, :, :, 1:], torch.full_like(y2[:, :, :, 1:], 2.0 ** -9))
+    # random data: same accuracy class as the two-part kernel (the activations still carry 16 bits), all N slices
+    x = _mk32(3, 144, 4, 4, 57)
+    g = torch.Generator().manual_seed(58)
+    w = (torch.randn(160, 144, 3, 3, generator=g) / 36).cuda()
+    b = torch.randn(160, generator=g).cuda()
+    y = ops.conv3x3(x, w, b, lrelu=True, exact_w=True)
+    ref = F.leaky_relu(F.conv2d(x.double(), w.double(), b.double(), padding=1), 0.2)
+    assert ((y.double() - ref).norm() / ref.norm()).item() <= 2e-5
+
+
 @pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 32, 128, 4, 4), (2, 128, 112, 8, 8), (1, 96, 80, 32, 32), (2, 32, 16, 24, 40)])
 def test_split_fused_epilogue_and_upsample(B, Cin, Cout, H, W):
     from musicgan_b200.networks import ops
@@ -284,20 +307,19 @@ def test_split_fused_epilogue_and_upsample(B, Cin, Cout, H, W):
 
 
 def test_split_weights_in_the_bf16_kernel():
-    """flag 16: weights enter as hi + lo bf16 pairs.  A centre-tap weight of 256.5 (hi = 256, lo = 0.5) on a
-    channel-diagonal convolution must give bf16(256.5 * x), not bf16(256 * x)."""
+    """flag 16: weights enter as hi + lo bf16 pairs.  On a constant image a centre tap of 256.5 (hi = 256, lo = 0.5) and a
+    left tap of -256 must leave 0.5 in the interior -- the low halves alone; with plain bf16 weights the result is 0."""
     from musicgan_b200.networks import ops
     for C in (16, 48, 80):
-        x = _mk(2, C, 32, 24, 61)
+        x = torch.ones(2, C, 32, 24, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
         w = torch.zeros(C, C, 3, 3, device="cuda")
         w[torch.arange(C), torch.arange(C), 1, 1] = 256.5
+        w[torch.arange(C), torch.arange(C), 1, 0] = -256.0
         y = ops.conv3x3(x, w, None, split_w=True).float()
-        want = (256.5 * x.float()).bfloat16().float()
-        plain = (256.0 * x.float()).bfloat16().float()
-        assert (y == want).float().mean().item() >= 0.999
-        assert (want != plain).float().mean().item() >= 0.2        # the test can tell the two apart
+        assert torch.equal(y[:, :, :, 1:], torch.full_like(y[:, :, :, 1:], 0.5))
+        assert torch.equal(y[:, :, :, 0], torch.full_like(y[:, :, :, 0], 256.0))      # left tap in the padding: bf16(256.5)
         y1 = ops.conv3x3(x, w, None).float()                       # without the flag: bf16(w) = 256
-        assert (y1 == plain).float().mean().item() >= 0.999
+        assert torch.equal(y1[:, :, :, 1:], torch.zeros_like(y1[:, :, :, 1:]))
     # and through the PixelNorm epilogue of the widest such layer (all Cout in one slice, weights 2 x 92 KB)
     x = _mk(1, 80, 32, 32, 62)
     g = torch.Generator().manual_seed(63)

@@ -9,8 +9,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _run(K, N, mode, Ra=128, row_off=0, grp_rows=8, seed=0):
-    from musicgan_b200 import _lib
-    l = _lib.lib()
+    from musicgan_b200 import _lib, build
+    l = ctypes.CDLL(build.DEBUG_LIB)          # test-only probes: their own library, not the product .so
     l.mg_debug_umma_gemm.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 + [ctypes.c_void_p]
     g = torch.Generator().manual_seed(seed)
     if mode == 0:
