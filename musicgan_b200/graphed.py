@@ -70,6 +70,8 @@ class GraphedSteps:
     def _critic_body(self):
         gen, disc, alpha, n = self.gen, self.disc, self.alpha, self.batch
         z = self.z if self.z is not None else th.randn(self.z_shape, device=self.x_real.device)
+        ops.prepack(gen)                           # one launch re-packs every weight of a network after its last update
+        ops.prepack(disc)                          # (from here on both branches below only read the packed copies)
         with th.no_grad():
             x_fake = gen(z, alpha)
         params = [p for p in disc.parameters()]
@@ -79,7 +81,6 @@ class GraphedSteps:
             gp = disc.gradient_penalty(self.x_real, x_fake, alpha, eps=self.eps)
             grads = th.autograd.grad(d_loss + gp, params, allow_unused=True)
         else:
-            ops.prepack(disc)                      # from here on both branches only read the packed weights
             main, branch = th.cuda.current_stream(), self._branch
             branch.wait_stream(main)
             with th.cuda.stream(branch):
@@ -100,6 +101,8 @@ class GraphedSteps:
         # only G's gradients are needed (the reference computes and discards D's, train.py:208-214): with the critic
         # frozen its weight-gradient kernels are not even launched
         params = [p for p in gen.parameters()]
+        ops.prepack(gen)
+        ops.prepack(disc)
         with frozen(disc):
             out_fake = disc(gen(z, alpha), alpha)
             g_loss = networks.wasserstein_generator_loss(out_fake)
@@ -154,12 +157,15 @@ class GraphedSteps:
         ops.prepack(self.gen)
         th.cuda.synchronize()
         ops.invalidate_pack_cache()
+        # kernel scratch requested during the captures comes from the graphs' private pool: it is kept in a dict that
+        # lives and dies with this object (ops.capture_workspaces), not in the process-wide workspace cache
+        self._ws = {}
         self._gd = th.cuda.CUDAGraph()
-        with th.cuda.graph(self._gd):
+        with ops.capture_workspaces(self._ws), th.cuda.graph(self._gd):
             self.d_stats = self._critic_body()
         ops.invalidate_pack_cache()
         self._gg = th.cuda.CUDAGraph()
-        with th.cuda.graph(self._gg, pool=self._gd.pool()):
+        with ops.capture_workspaces(self._ws), th.cuda.graph(self._gg, pool=self._gd.pool()):
             self.g_stats = self._generator_body()
         ops.invalidate_pack_cache()
 

@@ -90,12 +90,37 @@ def _l():
     return l
 
 
+# Scratch buffers are cached per (purpose, device, stream).  A buffer first requested DURING a CUDA-graph capture is carved
+# from that graph's private memory pool and dies with the graph: such buffers live in a dict owned by the capturing object
+# (graphed.GraphedSteps installs it with `capture_workspaces`), never in the process-wide cache -- a later graph or eager
+# call must not be handed an address inside a destroyed graph's pool.
+_capture_ws = [None]
+
+
+class capture_workspaces:
+    def __init__(self, owner_dict):
+        self.d = owner_dict
+
+    def __enter__(self):
+        self.prev, _capture_ws[0] = _capture_ws[0], self.d
+
+    def __exit__(self, *exc):
+        _capture_ws[0] = self.prev
+        return False
+
+
 def _workspace(dev, nbytes: int, tag: str = "pack") -> th.Tensor:
     key = (tag, dev.index, th.cuda.current_stream(dev).cuda_stream)
-    ws = _ws_cache.get(key)
+    cache = _ws_cache
+    if th.cuda.is_current_stream_capturing():
+        if _capture_ws[0] is None:
+            raise RuntimeError("musicgan_b200: a kernel workspace was requested inside a CUDA-graph capture outside "
+                               "ops.capture_workspaces(...) (use graphed.GraphedSteps)")
+        cache = _capture_ws[0]
+    ws = cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = th.empty(max(nbytes, 1 << 20), dtype=th.uint8, device=dev)
-        _ws_cache[key] = ws
+        cache[key] = ws
     return ws
 
 
@@ -124,7 +149,9 @@ def _packed_weights(w: th.Tensor, cin: int, cout: int, kind):
     cin / cout are those of the GEMM that will run.  The cache lives and dies with the Parameter (a global dict keyed by
     address would hand one model's weights to the next model allocated at the same address).  Temporaries
     (double-backward operands) are never cached."""
-    if os.environ.get("MG_NO_PACK_CACHE") or not (w.is_leaf and w.requires_grad):
+    # parameters only (temporaries change every call); a parameter frozen for one step (train_step.frozen: the critic
+    # inside the generator step) is still a parameter
+    if os.environ.get("MG_NO_PACK_CACHE") or not (w.is_leaf and (w.requires_grad or getattr(w, "_mg_frozen", False))):
         return None
     cache = getattr(w, "_mg_packed", None)
     if cache is None:
@@ -138,7 +165,13 @@ def _packed_weights(w: th.Tensor, cin: int, cout: int, kind):
     l = _l()
     split = kind[0] == "split"
     nbytes = l.mg_conv3x3_split_workspace_bytes(cin, cout) if split else l.mg_conv3x3_workspace_bytes(cin, cout)
-    buf = hit[1] if (hit is not None and hit[1].device == w.device) else th.empty(nbytes, dtype=th.uint8, device=w.device)
+    if hit is not None and hit[1].device == w.device:
+        buf = hit[1]
+    else:
+        if th.cuda.is_current_stream_capturing():      # would live in (and die with) the capturing graph's memory pool
+            raise RuntimeError("musicgan_b200: a packed-weight buffer was first requested inside a CUDA-graph capture; run "
+                               "the step once eagerly before capturing (graphed.GraphedSteps warms up)")
+        buf = th.empty(nbytes, dtype=th.uint8, device=w.device)
     with th.cuda.device(w.device):
         if split:
             _lib.check(l.mg_conv3x3_split_pack_weights(w.data_ptr(), cin, cout, kind[1], buf.data_ptr(), buf.numel(),
@@ -160,7 +193,7 @@ def prepack(module) -> None:
     entries = []
     for p in module.parameters():
         cache = getattr(p, "_mg_packed", None)
-        if cache and p.is_cuda and p.requires_grad:
+        if cache and p.is_cuda:
             for key, (stamp, buf) in cache.items():
                 entries.append((p, key, buf))
     if not entries:

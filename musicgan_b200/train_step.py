@@ -40,10 +40,12 @@ class frozen:
     def __enter__(self):
         for p in self.params:
             p.requires_grad_(False)
+            p._mg_frozen = True          # still a parameter for the packed-weight cache (networks/ops.py)
 
     def __exit__(self, *exc):
         for p in self.params:
             p.requires_grad_(True)
+            p._mg_frozen = False
         return False
 
 
