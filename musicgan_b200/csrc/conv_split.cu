@@ -122,40 +122,57 @@ k_conv3x3_split(const SplitParams p) {
         }
         const int w_rows = 18 * p.wparts;            // [tap][part][chunk] rows of packed weights per channel group
         const int w_items = w_rows * nt;             // 16-byte chunks of them in this slice
-        int slot = 0; uint32_t ph = 0;
-        for (int cg = 0; cg < n_cg; ++cg) {
-            mbar_wait(&empty[slot], ph ^ 1u);
-            unsigned char* st = smem + (size_t)slot * p.stage_bytes;
-            // weights: [tap][part][chunk] rows of Cout entries; this slice takes nt of them starting at n0
-            const uint4* wsrc = p.wpack + (size_t)cg * w_rows * p.Cout + n0;
-            const uint32_t sB = smem_u32(st + 2 * kSplitAPlane);
-            for (int i = pt; i < w_items; i += 128) {
-                const int q = i / nt, n = i - q * nt;
-                cp_async16_full(sB + (uint32_t)i * 16u, wsrc + (size_t)q * p.Cout + n);
-            }
-            // halo: fp32 -> (hi, lo) bf16 planes
-            float4 va[3], vb[3];
+        // The halo values are read with plain loads (they are converted before they reach shared memory), so a thread
+        // that loaded, converted and stored one channel group after the other would pay one memory round trip per group
+        // (measured: 2-3 us per group, 15-20 us for a 160-channel layer whatever its size).  The loads of the next
+        // kPrefetch groups are therefore kept in flight in registers while the current group is converted.
+        constexpr int kPrefetch = 3;
+        float4 va[kPrefetch][3], vb[kPrefetch][3];
+        auto load_group = [&](int cg, float4 (&a)[3], float4 (&b4)[3]) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                a[k] = b4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (src_off[k] >= 0) {
-                    const float4* s = reinterpret_cast<const float4*>(img + src_off[k] + cg * 16);
-                    va[k] = __ldg(s); vb[k] = __ldg(s + 1);
+                    const float4* sp = reinterpret_cast<const float4*>(img + src_off[k] + cg * 16);
+                    a[k] = __ldg(sp); b4[k] = __ldg(sp + 1);
                 }
             }
+        };
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (src_off[k] != -2) {
-                    uint4 hi, lo;
-                    split8(va[k], vb[k], hi, lo);
-                    *reinterpret_cast<uint4*>(st + dst_off[k]) = hi;
-                    *reinterpret_cast<uint4*>(st + kSplitAPlane + dst_off[k]) = lo;
+        for (int d = 0; d < kPrefetch; ++d)
+            if (d < n_cg) load_group(d, va[d], vb[d]);
+        int slot = 0; uint32_t ph = 0;
+        for (int cg0 = 0; cg0 < n_cg; cg0 += kPrefetch) {
+#pragma unroll
+            for (int d = 0; d < kPrefetch; ++d) {
+                const int cg = cg0 + d;
+                if (cg < n_cg) {
+                    mbar_wait(&empty[slot], ph ^ 1u);
+                    unsigned char* st = smem + (size_t)slot * p.stage_bytes;
+                    // weights: [tap][part][chunk] rows of Cout entries; this slice takes nt of them starting at n0
+                    const uint4* wsrc = p.wpack + (size_t)cg * w_rows * p.Cout + n0;
+                    const uint32_t sB = smem_u32(st + 2 * kSplitAPlane);
+                    for (int i = pt; i < w_items; i += 128) {
+                        const int q = i / nt, n = i - q * nt;
+                        cp_async16_full(sB + (uint32_t)i * 16u, wsrc + (size_t)q * p.Cout + n);
+                    }
+                    // halo: fp32 -> (hi, lo) bf16 planes
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        if (src_off[k] != -2) {
+                            uint4 hi, lo;
+                            split8(va[d][k], vb[d][k], hi, lo);
+                            *reinterpret_cast<uint4*>(st + dst_off[k]) = hi;
+                            *reinterpret_cast<uint4*>(st + kSplitAPlane + dst_off[k]) = lo;
+                        }
+                    }
+                    fence_proxy_async();             // st.shared operands -> tensor core (async proxy) reads
+                    cp_async_arrive(&full[slot]);
+                    mbar_arrive(&full[slot]);
+                    if (cg + kPrefetch < n_cg) load_group(cg + kPrefetch, va[d], vb[d]);
+                    if (++slot == p.stages) { slot = 0; ph ^= 1u; }
                 }
             }
-            fence_proxy_async();                     // st.shared operands -> tensor core (async proxy) reads
-            cp_async_arrive(&full[slot]);
-            mbar_arrive(&full[slot]);
-            if (++slot == p.stages) { slot = 0; ph ^= 1u; }
         }
     } else if (warp == 8) {
         // ================= MMA issue =================
@@ -264,7 +281,12 @@ struct SplitPlan { int Nt, n_slices, stages, tmem_cols; unsigned stage_bytes; si
 static SplitPlan plan_split(int Cin, int Cout, bool full_n, int n_tiles, int wparts) {
     SplitPlan pl{};
     const size_t budget = 216 * 1024;
-    int slices = full_n ? 1 : (Cout + 79) / 80;
+    // slice width.  An M128 x N x K16 MMA from shared memory costs max(32, N / 2) cycles (the A tile is re-read by every
+    // MMA), so N <= 64 is as fast per CTA as it gets: layers with fewer tiles than SMs (latency bound) use narrow slices
+    // and a deep ring; layers with many tiles use the widest slice that still leaves two stages (fewer CTAs re-reading
+    // the same halo)
+    const int max_nt = n_tiles >= 148 ? 96 : (wparts == 3 ? 48 : 64);
+    int slices = full_n ? 1 : (Cout + max_nt - 1) / max_nt;
     // few tiles (tiny images): spread the weight traffic over more CTAs
     while (!full_n && n_tiles * slices < 96 && (Cout / 16 + slices) / (slices + 1) >= 2) ++slices;
     int Nt = ((Cout / 16 + slices - 1) / slices) * 16;
