@@ -21,8 +21,9 @@ inline FastDiv make_fast_div(int d) { FastDiv f; f.m = ((1ull << 40) / (unsigned
 __device__ __forceinline__ int fast_div(int n, FastDiv f) { return (int)(((unsigned long long)(unsigned)n * f.m) >> 40); }
 
 // Weight packing of the split-operand kernel (conv_split.cu):
-// fp32 [Cout][Cin][3][3] -> split bf16 [K/16][tap][part][2 chunks][N][8]   (N, K = GEMM channel counts); `wparts` = 2:
-// w = hi + lo (16 significand bits), 3: w = hi + mid + lo (24 bits, the fp32 weight exactly)
+// fp32 [Cout][Cin][3][3] -> split bf16 [K/16][tap][2 chunks][part][N][8]   (N, K = GEMM channel counts); `wparts` = 2:
+// w = hi + lo (16 significand bits), 3: w = hi + mid + lo (24 bits, the fp32 weight exactly).  The parts of a chunk sit
+// side by side so that ONE MMA against [hi | mid | lo] (GEMM N = parts * slice) computes all products of an activation half.
 //   transpose_flip = 0: B[n = co][k = ci] of tap (ky,kx) = w[co][ci][ky][kx]
 //   transpose_flip = 1: data gradient, B[n = ci][k = co] = w[co][ci][2-ky][2-kx]
 __device__ __forceinline__ void pack_weights_split_range(const float* __restrict__ w, int Cout, int Cin, int transpose_flip, int wparts,
@@ -42,11 +43,11 @@ __device__ __forceinline__ void pack_weights_split_range(const float* __restrict
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const float r1 = v - __bfloat162float(hi);
         const __nv_bfloat16 mid = __float2bfloat16_rn(r1), lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
-        // destination: [cg][tap][part][chunk][n][e]
-        const size_t base = ((size_t)(cg * 9 + tap) * wparts) * 2 * N * 8;
-        out[base + ((size_t)(0 * 2 + chunk) * N + n) * 8 + e] = hi;
-        out[base + ((size_t)(1 * 2 + chunk) * N + n) * 8 + e] = mid;
-        if (wparts == 3) out[base + ((size_t)(2 * 2 + chunk) * N + n) * 8 + e] = lo;
+        // destination: [cg][tap][chunk][part][n][e]
+        const size_t base = ((size_t)(cg * 9 + tap) * 2 + chunk) * wparts * N * 8;
+        out[base + ((size_t)0 * N + n) * 8 + e] = hi;
+        out[base + ((size_t)1 * N + n) * 8 + e] = mid;
+        if (wparts == 3) out[base + ((size_t)2 * N + n) * 8 + e] = lo;
     }
 }
 #endif

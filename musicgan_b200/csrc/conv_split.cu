@@ -6,18 +6,26 @@
 // the gradient discontinuously, and on the small-spatial layers (few pixels, nothing averages out) bf16 operands
 // (2^-9) move the WGAN-GP gradients by 2..10 % (scripts/precision_study.py).  Here every operand is the sum of two
 // bf16 numbers, x = hi + lo (16 significand bits), and the product is accumulated in fp32 as
-//       hi_x * hi_w  +  lo_x * hi_w  +  hi_x * lo_w                       (three tcgen05.mma per K step)
+//       hi_x * hi_w  +  lo_x * hi_w  +  hi_x * lo_w
 // which puts the pre-activation error near 2^-16: the masks agree with the fp32 reference's.  The critic's forward
 // convolutions go one step further (flag 32): w = hi + mid + lo carries the fp32 weight exactly and two more products
 // (lo_x * mid_w, hi_x * lo_w) are added -- with 1e5 pre-activations per step a few sit within 1e-5 of zero, and one
 // flipped mask in a 2 x 2-pixel layer moves the gradient-penalty gradient by percents (golden case stage2_b3).
+// The weight parts of a K chunk sit side by side in shared memory, so the products of one activation half are ONE
+// tcgen05.mma with GEMM N = parts * slice:  hi_x * [hi_w | mid_w | lo_w]  and  lo_x * [hi_w | mid_w]  -- two MMAs per
+// (tap, 16 channels) instead of three or five, into `parts` column groups of one TMEM accumulator that the epilogue
+// sums.  (Ablation, round 2: an M128 x N x K16 MMA fed from shared memory costs ~85 cycles whatever N <= 64 -- the
+// 4 KB activation tile is re-read by every instruction -- and those MMAs were 2/3 of the run time of the small layers;
+// separate accumulators per term did not help: the cost is issue throughput, not dependency latency.)
 //
 // Structure (small layers: simplicity over the last cycle):
 //   * one CTA = one 16 x 8 pixel tile of one image (GEMM M = 128) x one slice of output channels;
 //   * the reduction is streamed in groups of 16 input channels through a ring of shared-memory stages: per stage
-//     producers (4 warps) read the 18 x 10 halo of those channels in fp32, split it on the fly into the hi / lo bf16
-//     planes of the canonical no-swizzle UMMA layout (umma.cuh) and copy the packed split weights of the group
-//     (cp.async); zero padding, image borders and the nearest x2 upsampling of the input are resolved in the read;
+//     4 producer warps read the 18 x 10 halo of those channels in fp32 and split it on the fly into the hi / lo bf16
+//     planes of the canonical no-swizzle UMMA layout (umma.cuh) -- zero padding, image borders and the nearest x2
+//     upsampling of the input are resolved in the read -- while the 4 (until then idle) epilogue warps copy the packed
+//     weight parts of the group with cp.async.  (ncu, round 2: with ONE warp per scheduler doing both, the kernel was
+//     bound by the dependent-instruction latency of those warps -- issue slots 22 % busy, tensor pipe 12-22 %.)
 //   * one thread issues 9 taps x 3 MMAs (M128 x N x K16) per stage -- the taps are nine start addresses into the
 //     halo -- and commits the stage back to the producers;
 //   * 4 epilogue warps: tcgen05.ld -> + bias -> LeakyReLU(0.2) -> PixelNorm (layers.py:11-17) -> fp32 NHWC store.
@@ -36,8 +44,9 @@ constexpr int kSplitAPlane = 2 * kHaloPitch * 16; // bytes of one (hi or lo) pla
 
 struct SplitParams {
     const float* x;              // [B][Hin][Win][Cin] fp32
-    const uint4* wpack;          // [Cin/16][9 taps][wparts][2 chunks][Cout][8 bf16]
+    const uint4* wpack;          // [Cin/16][9 taps][2 chunks][wparts][Cout][8 bf16]
     int wparts;                  // 2: w = hi + lo; 3: w = hi + mid + lo
+    int ablate;                  // debug (MG_SPLIT_ABLATE): 1 no halo loads / conversion, 2 no weight copies, 4 no MMAs, 8 no stores
     const float* bias;           // [Cout] or null
     float* y;                    // [B][H][W][Cout] fp32
     __nv_bfloat16* y16;          // optional bf16 copy of y (operand of the bf16 weight-gradient kernel), or null
@@ -120,8 +129,6 @@ k_conv3x3_split(const SplitParams p) {
                 }
             }
         }
-        const int w_rows = 18 * p.wparts;            // [tap][part][chunk] rows of packed weights per channel group
-        const int w_items = w_rows * nt;             // 16-byte chunks of them in this slice
         // The halo values are read with plain loads (they are converted before they reach shared memory), so a thread
         // that loaded, converted and stored one channel group after the other would pay one memory round trip per group
         // (measured: 2-3 us per group, 15-20 us for a 160-channel layer whatever its size).  The loads of the next
@@ -132,7 +139,7 @@ k_conv3x3_split(const SplitParams p) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 a[k] = b4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (src_off[k] >= 0) {
+                if (src_off[k] >= 0 && !(p.ablate & 1)) {
                     const float4* sp = reinterpret_cast<const float4*>(img + src_off[k] + cg * 16);
                     a[k] = __ldg(sp); b4[k] = __ldg(sp + 1);
                 }
@@ -149,17 +156,10 @@ k_conv3x3_split(const SplitParams p) {
                 if (cg < n_cg) {
                     mbar_wait(&empty[slot], ph ^ 1u);
                     unsigned char* st = smem + (size_t)slot * p.stage_bytes;
-                    // weights: [tap][part][chunk] rows of Cout entries; this slice takes nt of them starting at n0
-                    const uint4* wsrc = p.wpack + (size_t)cg * w_rows * p.Cout + n0;
-                    const uint32_t sB = smem_u32(st + 2 * kSplitAPlane);
-                    for (int i = pt; i < w_items; i += 128) {
-                        const int q = i / nt, n = i - q * nt;
-                        cp_async16_full(sB + (uint32_t)i * 16u, wsrc + (size_t)q * p.Cout + n);
-                    }
                     // halo: fp32 -> (hi, lo) bf16 planes
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        if (src_off[k] != -2) {
+                        if (src_off[k] != -2 && !(p.ablate & 1)) {
                             uint4 hi, lo;
                             split8(va[d][k], vb[d][k], hi, lo);
                             *reinterpret_cast<uint4*>(st + dst_off[k]) = hi;
@@ -167,7 +167,6 @@ k_conv3x3_split(const SplitParams p) {
                         }
                     }
                     fence_proxy_async();             // st.shared operands -> tensor core (async proxy) reads
-                    cp_async_arrive(&full[slot]);
                     mbar_arrive(&full[slot]);
                     if (cg + kPrefetch < n_cg) load_group(cg + kPrefetch, va[d], vb[d]);
                     if (++slot == p.stages) { slot = 0; ph ^= 1u; }
@@ -176,7 +175,9 @@ k_conv3x3_split(const SplitParams p) {
         }
     } else if (warp == 8) {
         // ================= MMA issue =================
-        const uint32_t idesc = instr_desc_bf16(nt, false, false);
+        // hi_x against all weight parts (N = parts * nt), lo_x against all but the last (N = (parts - 1) * nt)
+        const uint32_t idesc_hi = instr_desc_bf16(p.wparts * nt, false, false);
+        const uint32_t idesc_lo = instr_desc_bf16((p.wparts - 1) * nt, false, false);
         int slot = 0; uint32_t ph = 0;
         uint32_t accum = 0;
         for (int cg = 0; cg < n_cg; ++cg) {
@@ -186,20 +187,16 @@ k_conv3x3_split(const SplitParams p) {
                 const uint32_t sA = smem_u32(smem + (size_t)slot * p.stage_bytes);
                 const uint64_t a_hi = smem_desc(sA, (uint32_t)kHaloPitch * 16u, kHaloW * 16u);
                 const uint64_t a_lo = smem_desc(sA + kSplitAPlane, (uint32_t)kHaloPitch * 16u, kHaloW * 16u);
-                const uint64_t b0 = smem_desc(sA + 2 * kSplitAPlane, (uint32_t)nt * 16u, 128u);
-                const uint32_t b_part = (uint32_t)(2 * nt);          // 16-byte units between the parts of a tap's weights
+                // B of a tap: [chunk][part][nt] x 16 bytes: K chunks parts * nt rows apart, 8-row groups 128 B apart
+                const uint64_t b0 = smem_desc(sA + 2 * kSplitAPlane, (uint32_t)(p.wparts * nt) * 16u, 128u);
+                const uint32_t b_tap = (uint32_t)(2 * p.wparts * nt);          // 16-byte units per tap
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
+                for (int tap = 0; tap < ((p.ablate & 4) ? 0 : 9); ++tap) {
                     const uint64_t off = (uint64_t)((tap / 3) * kHaloW + (tap % 3));
-                    const uint64_t b_hi = b0 + (uint64_t)(tap * p.wparts) * b_part, b_mid = b_hi + b_part;
-                    mma_bf16(tmem_base, a_hi + off, b_hi, idesc, accum);
+                    const uint64_t b = b0 + (uint64_t)tap * b_tap;
+                    mma_bf16(tmem_base, a_hi + off, b, idesc_hi, accum);
+                    mma_bf16(tmem_base, a_lo + off, b, idesc_lo, 1u);
                     accum = 1;
-                    mma_bf16(tmem_base, a_lo + off, b_hi, idesc, 1u);
-                    mma_bf16(tmem_base, a_hi + off, b_mid, idesc, 1u);
-                    if (p.wparts == 3) {
-                        mma_bf16(tmem_base, a_lo + off, b_mid, idesc, 1u);
-                        mma_bf16(tmem_base, a_hi + off, b_mid + b_part, idesc, 1u);
-                    }
                 }
                 mma_commit(&empty[slot]);
                 if (cg + 1 == n_cg) mma_commit(acc_full);
@@ -208,7 +205,27 @@ k_conv3x3_split(const SplitParams p) {
             if (++slot == p.stages) { slot = 0; ph ^= 1u; }
         }
     } else {
-        // ================= epilogue =================
+        // ================= weight copies (while the reduction runs), then the epilogue =================
+        {
+            const int w_rows = 18 * p.wparts;        // [tap][chunk][part] rows of Cout entries per channel group
+            const int w_items = w_rows * nt;         // 16-byte chunks of them in this slice (nt per row, starting at n0)
+            // item i = q * nt + n -> source row q, column n; (q, n) advance by divmod(128, nt) per step: no division in the loop
+            const int q0 = tid / nt, c0 = tid - q0 * nt, dq = 128 / nt, dn = 128 - dq * nt;
+            int slot = 0; uint32_t ph = 0;
+            for (int cg = 0; cg < n_cg; ++cg) {
+                mbar_wait(&empty[slot], ph ^ 1u);
+                const uint4* wsrc = p.wpack + (size_t)cg * w_rows * p.Cout + n0;
+                const uint32_t sB = smem_u32(smem + (size_t)slot * p.stage_bytes + 2 * kSplitAPlane);
+                int q = q0, n = c0;
+                for (int i = tid; i < ((p.ablate & 2) ? 0 : w_items); i += 128) {
+                    cp_async16_full(sB + (uint32_t)i * 16u, wsrc + (size_t)q * p.Cout + n);
+                    q += dq; n += dn;
+                    if (n >= nt) { n -= nt; ++q; }
+                }
+                cp_async_arrive(&full[slot]);
+                if (++slot == p.stages) { slot = 0; ph ^= 1u; }
+            }
+        }
         const int m = warp * 32 + lane;              // TMEM lane == pixel of the tile
         const int oy = tyi * kTileH + (m >> 3), ox = txi * kTileW + (m & 7);
         const bool valid = oy < p.H && ox < p.W;
@@ -216,13 +233,24 @@ k_conv3x3_split(const SplitParams p) {
         const int units = nt >> 4;
         mbar_wait(acc_full, 0);
         tc_fence_after();
+        const int n_terms = p.wparts;
+        auto load_sum16 = [&](int u, float (&v)[16]) {       // sum over the column groups of the weight parts, 16 channels
+            tmem_ld16(taddr + u * 16, v);
+            tmem_wait_ld();
+            for (int t = 1; t < n_terms; ++t) {
+                float w16[16];
+                tmem_ld16(taddr + t * nt + u * 16, w16);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += w16[j];
+            }
+        };
         float scale = 1.0f;
         if (kPN) {
             float ss = 0.0f;
             for (int u = 0; u < units; ++u) {
                 float v[16];
-                tmem_ld16(taddr + u * 16, v);
-                tmem_wait_ld();
+                load_sum16(u, v);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     float t = v[j];
@@ -238,8 +266,7 @@ k_conv3x3_split(const SplitParams p) {
         __nv_bfloat16* dst16 = p.y16 ? p.y16 + pix * p.Cout + n0 : nullptr;
         for (int u = 0; u < units; ++u) {
             float v[16];
-            tmem_ld16(taddr + u * 16, v);
-            tmem_wait_ld();
+            load_sum16(u, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 float t = v[j];
@@ -247,7 +274,7 @@ k_conv3x3_split(const SplitParams p) {
                 if (kPN) t *= scale;
                 v[j] = t;
             }
-            if (valid) {
+            if (valid && !(p.ablate & 8)) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     *reinterpret_cast<float4*>(dst + u * 16 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -285,7 +312,8 @@ static SplitPlan plan_split(int Cin, int Cout, bool full_n, int n_tiles, int wpa
     // MMA), so N <= 64 is as fast per CTA as it gets: layers with fewer tiles than SMs (latency bound) use narrow slices
     // and a deep ring; layers with many tiles use the widest slice that still leaves two stages (fewer CTAs re-reading
     // the same halo)
-    const int max_nt = n_tiles >= 148 ? 96 : (wparts == 3 ? 48 : 64);
+    // (one MMA spans parts * Nt <= 256 columns: Nt <= 80 with three parts, <= 128 with two)
+    const int max_nt = n_tiles >= 148 ? (wparts == 3 ? 80 : 96) : (wparts == 3 ? 48 : 64);
     int slices = full_n ? 1 : (Cout + max_nt - 1) / max_nt;
     // few tiles (tiny images): spread the weight traffic over more CTAs
     while (!full_n && n_tiles * slices < 96 && (Cout / 16 + slices) / (slices + 1) >= 2) ++slices;
@@ -300,7 +328,7 @@ static SplitPlan plan_split(int Cin, int Cout, bool full_n, int n_tiles, int wpa
         if (stages > n_cg) stages = n_cg;
         pl.Nt = Nt; pl.n_slices = (Cout + Nt - 1) / Nt; pl.stages = stages; pl.stage_bytes = stage;
         pl.smem = (size_t)stages * stage + 256;
-        int cols = 32; while (cols < Nt) cols <<= 1;
+        int cols = 32; while (cols < wparts * Nt) cols <<= 1;      // `parts` column groups of Nt accumulator columns
         pl.tmem_cols = cols;
         return pl;
     }
@@ -350,6 +378,7 @@ int mg_conv3x3_split_f32(const float* x, const void* packed, const float* bias, 
     p.B = B; p.H = H; p.W = W; p.Hin = ups ? H / 2 : H; p.Win = ups ? W / 2 : W; p.Cin = Cin; p.Cout = Cout;
     p.upsample = ups; p.lrelu = flags & 1; p.pixelnorm = pn;
     p.Nt = pl.Nt; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols; p.stage_bytes = pl.stage_bytes; p.wparts = wparts;
+    p.ablate = getenv("MG_SPLIT_ABLATE") ? atoi(getenv("MG_SPLIT_ABLATE")) : 0;
     const bool ba = bias != nullptr || (flags & 1);
     auto kern = pn ? (ba ? k_conv3x3_split<true, true> : k_conv3x3_split<true, false>)
                    : (ba ? k_conv3x3_split<false, true> : k_conv3x3_split<false, false>);

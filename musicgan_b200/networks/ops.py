@@ -24,8 +24,27 @@ PRECISE_MAX_RES = int(os.environ.get("MG_PRECISE_MAX_RES", "64"))
 SPLIT_W = os.environ.get("MG_SPLIT_W", "1") != "0"
 
 
+# Inference (module in eval mode, autograd off: `generate`) has no gradients whose masks need protecting: the forward-only
+# mode keeps the fp32 split-operand path where it is nearly free (output height <= 32) and runs the rest on plain bf16
+# weights.  G output rel-L2 vs the fp32 oracle: see tests/test_networks_gpu.py::test_generator_inference_mode.
+FORWARD_ONLY_PRECISE_MAX_RES = int(os.environ.get("MG_INFER_PRECISE_MAX_RES", "32"))
+_forward_only = [False]
+
+
+class forward_only:
+    def __init__(self, on: bool):
+        self.on = bool(on)
+
+    def __enter__(self):
+        self.prev, _forward_only[0] = _forward_only[0], self.on
+
+    def __exit__(self, *exc):
+        _forward_only[0] = self.prev
+        return False
+
+
 def is_precise(h_out: int) -> bool:
-    return h_out <= PRECISE_MAX_RES
+    return h_out <= (FORWARD_ONLY_PRECISE_MAX_RES if _forward_only[0] else PRECISE_MAX_RES)
 
 class PackJob(ctypes.Structure):        # mgPackJob of include/musicgan_b200.h
     _fields_ = [("w", c_void_p), ("out", c_void_p), ("cout_fwd", c_int), ("cin_fwd", c_int), ("flip", c_int), ("nt", c_int),
@@ -257,7 +276,7 @@ def conv3x3(x: th.Tensor, w: th.Tensor, bias=None, *, lrelu=False, pixelnorm=Fal
     precise = x.dtype == th.float32
     flags = (FLAG_LRELU if lrelu else 0) | (FLAG_PIXELNORM if pixelnorm else 0) | \
             (FLAG_UPSAMPLE_IN if upsample_in else 0) | (FLAG_DGRAD if dgrad else 0) | \
-            (FLAG_SPLIT_W if (split_w and SPLIT_W and not precise) else 0)
+            (FLAG_SPLIT_W if (split_w and SPLIT_W and not precise and not _forward_only[0]) else 0)
     y = th.empty((B, cout, H, W), dtype=x.dtype, device=x.device, memory_format=th.channels_last)
     inv = th.empty((B, H, W), dtype=th.float32, device=x.device) if (pixelnorm and want_inv_norm) else None
     l = _l()

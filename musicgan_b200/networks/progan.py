@@ -109,6 +109,10 @@ class Generator(nn.Module):
 
     def forward(self, z: th.Tensor, alpha: float) -> th.Tensor:
         _require_cuda(z, "Generator.forward")
+        with fn.ops.forward_only(not self.training and not th.is_grad_enabled()):      # generate.py:38,54: eval(), no graph
+            return self._forward(z, alpha)
+
+    def _forward(self, z: th.Tensor, alpha: float) -> th.Tensor:
         out = z
         for i in range(self.curr_layer):
             out = self.__gen_blocks[i](out)

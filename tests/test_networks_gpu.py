@@ -61,6 +61,22 @@ def test_forward_vs_oracle(name):
         assert e_d <= TOL, e_d
 
 
+@pytest.mark.parametrize("name", ["stage5_b2", "stage7_b1"])
+def test_generator_inference_mode(name):
+    """generate.py:38,54 runs the generator in eval mode without a graph: the forward-only mode (plain bf16 weights above
+    32 x 32, no gradient masks to protect) must still give the reference's images within rel-L2 1e-2."""
+    stage, batch, alpha, z, z2, x_real, eps = case_inputs(name)
+    sd_g, sd_d = no.make_state("gen", stage, 11), no.make_state("disc", stage, 12)
+    gen, _ = build(stage, sd_g, sd_d)
+    gen.eval()
+    with torch.no_grad():
+        xf = gen(z.cuda(), 1.0)
+    ref = no.gen_forward(sd_g, z, 1.0, stage)
+    e = rel(xf, ref)
+    print(f"{name}: inference-mode G output rel-L2 {e:.2e}")
+    assert e <= TOL, e
+
+
 def _param_grads(module):
     return {k: p.grad for k, p in module.named_parameters() if p.grad is not None}
 
