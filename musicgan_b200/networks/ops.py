@@ -22,6 +22,9 @@ FLAG_LRELU, FLAG_PIXELNORM, FLAG_UPSAMPLE_IN, FLAG_DGRAD, FLAG_SPLIT_W, FLAG_W3 
 PRECISE_MAX_RES = int(os.environ.get("MG_PRECISE_MAX_RES", "64"))
 # Forward convolutions of the bf16 layers take their weights as hi + lo bf16 pairs (flag 16); 0 = plain bf16 weights.
 SPLIT_W = os.environ.get("MG_SPLIT_W", "1") != "0"
+# ... up to this output height.  Measured on B200: leaving the 512 x 512 layers on plain bf16 weights (256) buys 1 % of step
+# time and moves the stage-7 batch-1 generator-step gradient from 7.8e-3 to 9.1e-3 of the oracle's: not taken.
+SPLIT_W_MAX_RES = int(os.environ.get("MG_SPLIT_W_MAX_RES", "512"))
 
 
 # Inference (module in eval mode, autograd off: `generate`) has no gradients whose masks need protecting: the forward-only
@@ -276,7 +279,7 @@ def conv3x3(x: th.Tensor, w: th.Tensor, bias=None, *, lrelu=False, pixelnorm=Fal
     precise = x.dtype == th.float32
     flags = (FLAG_LRELU if lrelu else 0) | (FLAG_PIXELNORM if pixelnorm else 0) | \
             (FLAG_UPSAMPLE_IN if upsample_in else 0) | (FLAG_DGRAD if dgrad else 0) | \
-            (FLAG_SPLIT_W if (split_w and SPLIT_W and not precise and not _forward_only[0]) else 0)
+            (FLAG_SPLIT_W if (split_w and SPLIT_W and not precise and not _forward_only[0] and H <= SPLIT_W_MAX_RES) else 0)
     y = th.empty((B, cout, H, W), dtype=x.dtype, device=x.device, memory_format=th.channels_last)
     inv = th.empty((B, H, W), dtype=th.float32, device=x.device) if (pixelnorm and want_inv_norm) else None
     l = _l()
