@@ -48,7 +48,8 @@ struct ConvParams {
     int consumer_fence;
     int ablate;                  // debug (MG_CONV_ABLATE): 1 no halo copies, 2 no MMAs, 4 no epilogue work, 8 no global stores
     int epi_warps;               // 4 or 8 epilogue warps; producers are the next 4 warps, then the MMA warp
-    int parts;                   // 1: bf16 weights; 2: weights as hi + lo bf16 pairs, two MMA sweeps over the same halo
+    int parts;                   // 1: bf16 weights; 2: weights as hi + lo bf16 pairs side by side along N: ONE MMA per tap and
+                                 //    K step computes x * [w_hi | w_lo] into two column groups that the epilogue sums
 };
 
 // warp roles: [0, E) epilogue (E = 4, or 8 = two per TMEM lane quarter with half the columns each), [E, E+4) producers,
@@ -65,7 +66,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // K = 16 MMA per tile whose A operand is a constant tile (columns 0 and 1 = 1.0) and whose B operand holds the bias
 // split in two bf16 terms (hi + lo: 16 mantissa bits) in K rows 0 and 1.
 // kOcc4: the 9-warp shape compiled for 4 CTAs per SM (56 registers per thread, a shorter chunk table in the producers).
-template <bool kPN, bool kBA, bool kOcc4>
+// kW2: hi + lo weights (two accumulator column groups summed by the epilogue); never combined with kOcc4 (registers).
+template <bool kPN, bool kBA, bool kOcc4, bool kW2>
 __global__ void __launch_bounds__(kOcc4 ? 288 : kConvThreads, kOcc4 ? 4 : 2)
 k_conv3x3(const ConvParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -76,8 +78,8 @@ k_conv3x3(const ConvParams p) {
     const int nt = min(p.Nt, p.Cout - n0);
     const int kEpiWarps = p.epi_warps, kProdWarp0 = kEpiWarps, kMmaWarp = kEpiWarps + 4;
 
-    uint4* sW = reinterpret_cast<uint4*>(smem);                    // [parts][9 taps][nch][nt] + bias pseudo-tap [2][nt]
-    uint4* sOnes = sW + (9 * nch * p.parts + 2) * nt;              // [2][128]: the constant A tile of the bias MMA
+    uint4* sW = reinterpret_cast<uint4*>(smem);                    // [9 taps][nch][parts][nt] + bias pseudo-tap [2][parts][nt]
+    uint4* sOnes = sW + (9 * nch + 2) * p.parts * nt;              // [2][128]: the constant A tile of the bias MMA
     uint4* sA0 = sOnes + 256;
     float* sPart = reinterpret_cast<float*>(sA0 + (size_t)p.stages * nch * p.halo_pitch);      // [2][128] PixelNorm partial sums
     uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + 256);
@@ -120,11 +122,12 @@ k_conv3x3(const ConvParams p) {
             for (int i = pt; i < total; i += 128) cp_async16(sw_addr + (uint32_t)i * 16u, src + i, 16u);
             if (kBA) {
                 uint4* sB = sW + 9 * nch * nt * p.parts;
-                for (int i = pt; i < nt; i += 128) {
-                    const float bv = p.bias ? p.bias[n0 + i] : 0.0f;
+                const int nn = p.parts * nt;                              // GEMM N: the bias sits in the first column group
+                for (int i = pt; i < nn; i += 128) {
+                    const float bv = (p.bias && i < nt) ? p.bias[n0 + i] : 0.0f;
                     const __nv_bfloat16 hi = __float2bfloat16_rn(bv), lo = __float2bfloat16_rn(bv - __bfloat162float(hi));
                     sB[i] = make_uint4((uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16), 0u, 0u, 0u);
-                    sB[nt + i] = make_uint4(0u, 0u, 0u, 0u);
+                    sB[nn + i] = make_uint4(0u, 0u, 0u, 0u);
                 }
                 sOnes[pt] = make_uint4(0x3F803F80u, 0u, 0u, 0u);          // bf16 (1.0, 1.0) in K columns 0 and 1
                 sOnes[128 + pt] = make_uint4(0u, 0u, 0u, 0u);
@@ -201,11 +204,12 @@ k_conv3x3(const ConvParams p) {
         // Descriptors only differ in their 14-bit start-address field, so they are formed by integer additions:
         //   A: slot base + tap offset (ky*10 + kx positions) + k-step * 2 * kHaloPitch      (16-byte units)
         //   B: weights are packed [tap][k chunk][n] -> the descriptor simply advances by 2*nt per MMA
-        const uint32_t idesc = instr_desc_bf16(nt, false, false);
+        const int nn = p.parts * nt;                   // GEMM N of every MMA: [w | w_lo] side by side when parts == 2
+        const uint32_t idesc = instr_desc_bf16(nn, false, false);
         const uint64_t a_desc0 = smem_desc(smem_u32(sA0), (uint32_t)p.halo_pitch * 16u, kHaloW * 16u);
-        const uint64_t b_desc0 = smem_desc(smem_u32(sW), (uint32_t)nt * 16u, 128u);
+        const uint64_t b_desc0 = smem_desc(smem_u32(sW), (uint32_t)nn * 16u, 128u);
         const uint64_t ones_desc = smem_desc(smem_u32(sOnes), 128u * 16u, 128u);
-        const uint32_t slot_units = (uint32_t)(nch * p.halo_pitch), b_step = (uint32_t)(2 * nt);
+        const uint32_t slot_units = (uint32_t)(nch * p.halo_pitch), b_step = (uint32_t)(2 * nn);
         const uint32_t a_kstep = 2u * (uint32_t)p.halo_pitch;
         const int ksteps = nch >> 1;
         mbar_wait(w_full, 0);
@@ -221,20 +225,20 @@ k_conv3x3(const ConvParams p) {
                     const uint64_t da_blk = a_desc0 + (uint64_t)(slot * slot_units + blk * (kTileH * kHaloW));
                     uint64_t db = b_desc0;
                     uint32_t accum = 0;
-                    // parts == 2: a second sweep of the same halo against the low halves of the weights (w = hi + lo:
-                    // 16 significand bits, so that LeakyReLU masks agree with the fp32 reference's; the tensor pipe is
-                    // far from saturated on these HBM-bound layers)
+                    // parts == 2 (w = hi + lo, 16 significand bits, so that LeakyReLU masks agree with the fp32
+                    // reference's): the low halves sit beside the high halves along N, the SAME MMA computes both
+                    // products.  (These small MMAs cost ~85 cycles each whatever N <= 64 -- the 4 KB activation tile is
+                    // re-read from shared memory by every instruction -- and their count is what bounds the layer: a
+                    // second sweep over the halo, as first written, cost 30-60 % on the 128 x 128 / 256 x 256 layers.)
                     if (!(p.ablate & 2))
-                    for (int part = 0; part < p.parts; ++part) {
 #pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
-                            uint64_t da = da_blk + (uint64_t)((tap / 3) * kHaloW + (tap % 3));
-                            for (int kk = 0; kk < ksteps; ++kk) {
-                                mma_bf16(d, da, db, idesc, accum);
-                                accum = 1;
-                                da += a_kstep;
-                                db += b_step;
-                            }
+                    for (int tap = 0; tap < 9; ++tap) {
+                        uint64_t da = da_blk + (uint64_t)((tap / 3) * kHaloW + (tap % 3));
+                        for (int kk = 0; kk < ksteps; ++kk) {
+                            mma_bf16(d, da, db, idesc, accum);
+                            accum = 1;
+                            da += a_kstep;
+                            db += b_step;
                         }
                     }
                     if (kBA) mma_bf16(d, ones_desc, db, idesc, 1u);      // + bias (db now points at the bias pseudo-tap)
@@ -281,12 +285,23 @@ k_conv3x3(const ConvParams p) {
                 const bool valid = oy < p.H && ox < p.W;
                 const bool last_blk = blk + 1 == p.mb;
                 const uint32_t taddr = tmem_base + acc * acc_stride + blk * p.blk_stride + ((uint32_t)(quarter * 32) << 16);
+                // 16 accumulator columns of unit u; with hi + lo weights the sum of the two column groups
+                auto load16 = [&](int u, float* v) {
+                    tmem_ld16(taddr + u * 16, v);
+                    if (kW2) {
+                        float w16[16];
+                        tmem_ld16(taddr + nt + u * 16, w16);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += w16[j];
+                    }
+                };
                 float scale = 1.0f;
                 if (kPN) {
                     float ss = 0.0f;
                     for (int u = u0; u < u1; ++u) {
                         float v[16];
-                        tmem_ld16(taddr + u * 16, v);
+                        load16(u, v);
                         tmem_wait_ld();
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
@@ -327,15 +342,15 @@ k_conv3x3(const ConvParams p) {
                 int u = u0;
                 for (; u + 2 <= u1; u += 2) {
                     float v[32];
-                    tmem_ld16(taddr + u * 16, v);
-                    tmem_ld16(taddr + u * 16 + 16, v + 16);
+                    load16(u, v);
+                    load16(u + 1, v + 16);
                     tmem_wait_ld();
                     if (last_blk && u + 2 == u1) release();
                     if (!(p.ablate & 16)) { finish16(v, u); finish16(v + 16, u + 1); }
                 }
                 if (u < u1) {
                     float v[16];
-                    tmem_ld16(taddr + u * 16, v);
+                    load16(u, v);
                     tmem_wait_ld();
                     if (last_blk) release();
                     if (!(p.ablate & 16)) finish16(v, u);
@@ -352,8 +367,8 @@ k_conv3x3(const ConvParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight packing: fp32 [Cout][Cin][3][3]  ->  bf16 [slice][part][tap][Cin/8][nt][8]   (part 0 = bf16(w), part 1 =
-// bf16(w - part 0) when parts == 2)
+// weight packing: fp32 [Cout][Cin][3][3]  ->  bf16 [slice][tap][Cin/8][part][nt][8]   (part 0 = bf16(w), part 1 =
+// bf16(w - part 0) when parts == 2: side by side along the GEMM N dimension)
 //   transpose_flip = 0 (fprop):  B[n = co][k = ci] of tap (ky,kx) = w[co][ci][ky][kx]
 //   transpose_flip = 1 (dgrad):  the data gradient is a 3x3 convolution of dY with
 //                                w'[ci][co][ky][kx] = w[co][ci][2-ky][2-kx]; n runs over ci, k over co.
@@ -383,9 +398,10 @@ __device__ __forceinline__ void pack_weights_range(const float* __restrict__ w, 
                 if (!transpose_flip) v = w[(((size_t)n * Cin + k) * 3 + ky) * 3 + kx];
                 else v = w[(((size_t)k * Cin + n) * 3 + (2 - ky)) * 3 + (2 - kx)];
                 const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-                // slice base in the output is parts * base; part 1 follows the cnt elements of part 0
-                out[(size_t)parts * base * 8 + (size_t)q * 8 + e] = hi;
-                if (parts == 2) out[(size_t)parts * base * 8 + (size_t)cnt * 8 + (size_t)q * 8 + e] = __float2bfloat16_rn(v - __bfloat162float(hi));
+                // slice base in the output is parts * base; within the slice [tap][chunk][part][n_local]
+                const size_t o = ((size_t)parts * base + ((size_t)tc * parts) * nt + n_local) * 8 + e;
+                out[o] = hi;
+                if (parts == 2) out[o + (size_t)nt * 8] = __float2bfloat16_rn(v - __bfloat162float(hi));
                 break;
             }
             base += cnt; ++slice;
@@ -425,9 +441,9 @@ static ConvPlan plan_conv(int Cin, int Cout, bool need_full_n, int H = 0, int pa
     int Nt = 0;
     for (int stages = 2; stages >= 1 && !Nt; --stages)
         for (int n = Cout; n >= (need_full_n ? Cout : 16); n -= 16)
-            if ((size_t)9 * nch * n * 16 * parts + (size_t)stages * nch * kHaloPitch * 16 + (size_t)2 * n * 16 + 4096 + 1024 + 384 <= budget) { Nt = n; break; }
+            if ((size_t)(9 * nch + 2) * n * 16 * parts + (size_t)stages * nch * kHaloPitch * 16 + 4096 + 1024 + 384 <= budget) { Nt = n; break; }
     if (!Nt || (need_full_n && Nt != Cout)) return pl;
-    const size_t base = (size_t)9 * nch * Nt * 16 * parts + (size_t)2 * Nt * 16 + 4096 + 1024 + 384;   // weights, bias pseudo-tap, constant A tile, PixelNorm partials, barriers
+    const size_t base = (size_t)(9 * nch + 2) * Nt * 16 * parts + 4096 + 1024 + 384;   // weights, bias pseudo-tap, constant A tile, PixelNorm partials, barriers
     // 2. shape of one pipeline step.  The warps of a CTA are few and specialised, so (a) several CTAs share an SM
     //    (registers: 72/thread -> 3 CTAs of 9 warps with 4 epilogue warps, or 2 CTAs of 13 warps with 8) and (b) on
     //    the large images a step covers `mb` vertically stacked 16 x 8 blocks, which divides the per-step costs
@@ -443,13 +459,14 @@ static ConvPlan plan_conv(int Cin, int Cout, bool need_full_n, int H = 0, int pa
             const int mb = c[0], occ = c[1];
             if (pass == 0 && ((force_occ && occ != force_occ) || (force_mb && mb != force_mb))) continue;
             if (mb > 1 && H < kTileH * mb) continue;
+            if (occ == 4 && parts == 2) continue;       // the hi + lo epilogue does not fit the 56-register shape
             const int halo_pos = (kTileH * mb + 2) * kHaloW, pitch = halo_pos + 6;
             if (mb > 1 && halo_pos * nch > 12 * 128) continue;
             if (occ == 4 && halo_pos * nch > 6 * 128) continue;
             const size_t stage_b = (size_t)nch * pitch * 16;
             const size_t cap = occ == 4 ? 54 * 1024 : occ == 3 ? 73 * 1024 : occ == 2 ? 110 * 1024 : budget;
             const int cols_cap = occ >= 3 ? 128 : occ == 2 ? 256 : 512;
-            const int blk_stride = (Nt + 31) & ~31, acc_stride = mb * blk_stride;
+            const int blk_stride = (parts * Nt + 31) & ~31, acc_stride = mb * blk_stride;      // parts column groups per block
             const int min_stages = occ > 1 ? ((mb > 1 || occ == 4) ? 3 : 4) : 1;
             if (occ > 1 && 2 * acc_stride > cols_cap) continue;
             if (acc_stride > cols_cap || base + min_stages * stage_b > cap) continue;
@@ -572,8 +589,15 @@ int mg_conv3x3_bf16(const void* x, const float* w_f32, const float* bias, void* 
     p.slope = (flags & 1) ? 0.2f : 1.0f;
     const bool ba = bias != nullptr || (flags & 1);
     const bool o4 = pl.occupancy == 4;
-    auto kern = o4 ? (pn ? (ba ? k_conv3x3<true, true, true> : k_conv3x3<true, false, true>) : (ba ? k_conv3x3<false, true, true> : k_conv3x3<false, false, true>))
-                   : (pn ? (ba ? k_conv3x3<true, true, false> : k_conv3x3<true, false, false>) : (ba ? k_conv3x3<false, true, false> : k_conv3x3<false, false, false>));
+    auto kern = o4 ? (pn ? (ba ? k_conv3x3<true, true, true, false> : k_conv3x3<true, false, true, false>)
+                         : (ba ? k_conv3x3<false, true, true, false> : k_conv3x3<false, false, true, false>))
+                   : (pn ? (ba ? k_conv3x3<true, true, false, false> : k_conv3x3<true, false, false, false>)
+                         : (ba ? k_conv3x3<false, true, false, false> : k_conv3x3<false, false, false, false>));
+    if (parts == 2) {
+        if (o4) return MG_ERR_UNSUPPORTED;
+        kern = pn ? (ba ? k_conv3x3<true, true, false, true> : k_conv3x3<true, false, false, true>)
+                  : (ba ? k_conv3x3<false, true, false, true> : k_conv3x3<false, false, false, true>);
+    }
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     int ctas = sm_count * pl.occupancy;
     if (const char* e = getenv("MG_CONV_MAX_CTAS")) { const int m = atoi(e); if (m > 0 && m < ctas) ctas = m; }   // tests: many steps per CTA
