@@ -227,7 +227,11 @@ def run_transform(args, rank, world, local):
                     "d2h_bytes_per_step": int(out_m.numel() + out_p.numel()) * 4, "clips_per_step": e2e_clips},
             "gpu_launches": int(sum(c for _, c in prof.values())),
             "roofline": {"bound": "hbm", "kernel": "k_stft", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s",
-                         "frac": achieved / pk["hbm"], "peak_source": pk["src"], "traffic": None,
+                         "frac": achieved / pk["hbm"], "peak_source": pk["src"],
+                         # dram__bytes_read + write of one k_stft launch (ncu --set full, profiles/r02_prof_stft_raw.csv:
+                         # 366.2 MB for 8 x 10 336 frames = 4 429 B / frame against 5 120 algorithmic: the tail of the
+                         # 4 KB / frame scratch is still in L2 when the launch ends), scaled to this launch's frames
+                         "traffic": 4429.0 * frames_per_step, "traffic_source": "ncu, bytes per frame x frames of this launch",
                          "step_achieved": step_gbs, "step_frac": step_gbs / pk["hbm"],
                          "kernel_ms": {k: round(v[0] / max(v[1], 1), 4) for k, v in prof.items()}},
             "cpu_baseline": {"value": cpu_v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",

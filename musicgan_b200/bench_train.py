@@ -174,7 +174,12 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
                      "achieved": gb_achieved if hbm_bound else tf_achieved, "peak": pk["hbm"] if hbm_bound else pk["tf_sus"],
                      "unit": "GB/s" if hbm_bound else "TFLOP/s",
                      "frac": (gb_achieved / pk["hbm"]) if hbm_bound else (tf_achieved / pk["tf_sus"]),
-                     "peak_source": pk["src"] + " (sustained)", "traffic": None,
+                     "peak_source": pk["src"] + " (sustained)",
+                     # the family's dominant launch, one ncu --set full capture (profiles/r02_prof_conv_fprop_d0c1_raw.csv):
+                     # D0.conv1 fprop at batch 8 moves 67.2 + 83.0 MB of DRAM traffic against 67.1 + 134.2 MB algorithmic
+                     # (part of the output still sits in the 126 MB L2 when the launch ends): no wasted re-reads
+                     "traffic": 150.2e6 * batch / 8.0, "traffic_source": "ncu dram__bytes read + write of D0.conv1 fprop per launch "
+                                                                          "(algorithmic 201.3 MB at batch 8)",
                      "tensor": {"achieved": tf_achieved, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": tf_achieved / pk["tf_sus"]},
                      "hbm": {"achieved": gb_achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": gb_achieved / pk["hbm"],
                              "bytes": "x read once + y written once per launch (wgrad: dy + x read), weights excluded"},
