@@ -115,8 +115,37 @@ def index_plan():
         print("   ", r)
 
 
+def scale_transform():
+    """Real-batch transform of the training loop (utils.py:70-82, train.py:139-140): ChannelMinMaxNorm ->
+    ChangeRange(-1, 1) -> torchvision Resize(512 / 2^k), run through the reference's own Grower at several growth stages."""
+    from music_gan import utils as ref_utils
+    g = th.Generator().manual_seed(4242)
+    x = th.rand(3, 2, 512, 512, generator=g, dtype=th.float64).float() * 3.0 - 1.0      # a batch of dataset chunks
+    out = {"seed": np.int64(4242)}
+    fade, lens = [1, 2, 2, 2, 2, 2, 2, 2], [1, 2, 3, 4, 5, 6, 7]
+    grower = ref_utils.Grower(7, fade, lens)
+    stage = 0
+    while True:
+        y = grower.scale_transform(x)
+        size = 4 * 2 ** stage
+        assert tuple(y.shape) == (3, 2, size, size), y.shape
+        stride = max(1, y.numel() // 8192)
+        out[f"stage{stage}"] = y.contiguous().view(-1)[::stride].numpy().copy()
+        out[f"stage{stage}_stride"] = np.int64(stride)
+        out[f"stage{stage}_digest"] = digest(y)
+        if stage == 7:
+            break
+        while not grower.grow(1):
+            pass
+        stage += 1
+    np.savez_compressed(os.path.join(GOLD, "scale_transform.npz"), **out)
+    print("scale_transform: stages 0..7 written")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["forward", "inverse", "index", "networks"]
+    which = sys.argv[1:] or ["forward", "inverse", "index", "networks", "scale"]
+    if "scale" in which:
+        scale_transform()
     if "forward" in which:
         audio_forward()
     if "inverse" in which:

@@ -79,3 +79,37 @@ def test_two_rank_allreduced_gradients_equal_single_process():
     for v in ret.values():
         assert v["real"] <= 1e-2 and v["gp"] <= 1e-2, v
         assert v["critic"] <= 1e-2, v
+
+
+def _gen_rank(rank, world, port, ckpt, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import musicgan_b200 as mg
+        torch.manual_seed(7)                 # the latent of ALL clips is drawn by every rank from the same stream
+        mg.generate(out_dir, 32, ckpt, nb_vec=1, nb_music=5)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_generate_shards_clips_over_two_ranks(tmp_path):
+    """generate shards CLIPS with no communication -- two ranks write exactly the files (names and samples)
+    that one process writes for the same latent draw (generate.py:47-65)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import musicgan_b200 as mg
+    from musicgan_b200 import networks
+    from musicgan_b200.audio import wavio
+    torch.manual_seed(0)
+    ckpt = str(tmp_path / "gen.pt")
+    torch.save(networks.Generator(32, end_layer=7).state_dict(), ckpt)
+    one, two = tmp_path / "one", tmp_path / "two"
+    torch.manual_seed(7)
+    mg.generate(str(one), 32, ckpt, nb_vec=1, nb_music=5)
+    mp.spawn(_gen_rank, args=(2, 29700 + os.getpid() % 1000, ckpt, str(two)), nprocs=2, join=True)
+    assert sorted(os.listdir(one)) == sorted(os.listdir(two)) == [f"sound_{i}.wav" for i in range(5)]
+    for i in range(5):
+        a, _ = wavio.load(str(one / f"sound_{i}.wav"))
+        b, _ = wavio.load(str(two / f"sound_{i}.wav"))
+        assert torch.equal(a, b), i

@@ -44,6 +44,28 @@ def test_create_dataset_matches_reference_numbering_and_content(tmp_path):
         mg.create_dataset(str(src / "*.wav"), str(src / "a.wav"))
 
 
+def test_create_dataset_packed_equals_reference_format_and_trains(tmp_path):
+    """`packed=True` writes one float32 shard per input file + index.json with the reference's chunk numbering;
+    the values are the float32 originals of the reference-format float64 files, and `train` reads it like any dataset."""
+    import musicgan_b200 as mg
+    from musicgan_b200.audio import wavio
+    from musicgan_b200.audio.dataset import AudioDataset
+    src, ref_out, packed_out = tmp_path / "wav", tmp_path / "ds_pt", tmp_path / "ds_packed"
+    src.mkdir()
+    for name, n in {"a": 270_001, "b": 100_000, "c": 140_000}.items():      # b is too short: skipped
+        g = torch.Generator().manual_seed(n)
+        wavio.save(str(src / f"{name}.wav"), torch.rand(1, n, generator=g) - 0.5, 44100)
+    mg.create_dataset(str(src / "*.wav"), str(ref_out))
+    mg.create_dataset(str(src / "*.wav"), str(packed_out), packed=True)
+    legacy, packed = AudioDataset(str(ref_out)), AudioDataset(str(packed_out))
+    assert len(legacy) == len(packed) == 3 and "index.json" in os.listdir(packed_out)
+    for i in range(3):           # < 10 chunks: the reference's lexicographic file order is the numeric order
+        assert torch.equal(packed[i].double(), legacy[i])
+    mg.train("t", str(packed_out), str(tmp_path / "run"), batch_size=2, nb_epoch=2, num_workers=2, save_every=2,
+             max_iterations=2, seed=0)
+    assert "gen_0.pt" in os.listdir(tmp_path / "run")
+
+
 def test_generate_writes_clips_of_the_reference_length(tmp_path):
     import musicgan_b200 as mg
     from musicgan_b200 import networks

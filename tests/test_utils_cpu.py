@@ -69,3 +69,40 @@ def test_grower_matches_reference_class():
     for _ in range(120):
         assert a.alpha == b.alpha
         assert a.grow(6) == b.grow(6)
+
+
+def _scale_case():
+    g = torch.Generator().manual_seed(4242)
+    return torch.rand(3, 2, 512, 512, generator=g, dtype=torch.float64).float() * 3.0 - 1.0
+
+
+def _check_scale_transform(device, golden_dir):
+    """utils.Grower.scale_transform (min-max, range, antialiased bilinear resize as two small GEMMs) against the
+    REFERENCE's own Grower / torchvision Compose at every growth stage (fixture: oracle/gen_golden.py scale)."""
+    import os
+    import numpy as np
+    from musicgan_b200.utils import Grower
+    gold = np.load(os.path.join(golden_dir, "scale_transform.npz"))
+    x = _scale_case().to(device)
+    grower = Grower(7, [1, 2, 2, 2, 2, 2, 2, 2], [1, 2, 3, 4, 5, 6, 7])
+    for stage in range(8):
+        y = grower.scale_transform(x)
+        size = 4 * 2 ** stage
+        assert tuple(y.shape) == (3, 2, size, size) and y.dtype == torch.float32
+        got = y.contiguous().view(-1)[::int(gold[f"stage{stage}_stride"])].cpu().numpy()
+        np.testing.assert_allclose(got, gold[f"stage{stage}"], rtol=2e-5, atol=4e-6)
+        d = gold[f"stage{stage}_digest"]
+        assert abs(y.double().sum().item() - d[0]) <= 2e-5 * d[1] + 1e-6
+        if stage < 7:
+            while not grower.grow(1):
+                pass
+
+
+def test_scale_transform_matches_reference_grower_cpu(golden_dir):
+    _check_scale_transform("cpu", golden_dir)
+
+
+@pytest.mark.gpu
+def test_scale_transform_matches_reference_grower_gpu(golden_dir):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    _check_scale_transform("cuda", golden_dir)
