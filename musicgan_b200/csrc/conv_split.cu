@@ -73,7 +73,7 @@ __device__ __forceinline__ void split8(const float4 a, const float4 b, uint4& hi
 }
 
 template <bool kPN, bool kBA>
-__global__ void __launch_bounds__(kSplitThreads, 1)
+__global__ void __launch_bounds__(kSplitThreads, 2)
 k_conv3x3_split(const SplitParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -133,7 +133,7 @@ k_conv3x3_split(const SplitParams p) {
         // that loaded, converted and stored one channel group after the other would pay one memory round trip per group
         // (measured: 2-3 us per group, 15-20 us for a 160-channel layer whatever its size).  The loads of the next
         // kPrefetch groups are therefore kept in flight in registers while the current group is converted.
-        constexpr int kPrefetch = 3;
+        constexpr int kPrefetch = 2;
         float4 va[kPrefetch][3], vb[kPrefetch][3];
         auto load_group = [&](int cg, float4 (&a)[3], float4 (&b4)[3]) {
 #pragma unroll
@@ -307,7 +307,10 @@ struct SplitPlan { int Nt, n_slices, stages, tmem_cols; unsigned stage_bytes; si
 
 static SplitPlan plan_split(int Cin, int Cout, bool full_n, int n_tiles, int wparts) {
     SplitPlan pl{};
-    const size_t budget = 216 * 1024;
+    // layers with several waves of tiles run TWO CTAs per SM (each gets half of the shared memory, i.e. a shorter ring):
+    // load, MMA and epilogue phases of neighbouring tiles then overlap; small layers keep one CTA with a deep ring
+    static const int two_cta_tiles = getenv("MG_SPLIT_2CTA_TILES") ? atoi(getenv("MG_SPLIT_2CTA_TILES")) : 0;
+    const size_t budget = (!full_n && two_cta_tiles > 0 && n_tiles >= two_cta_tiles ? 108 : 216) * 1024;
     // slice width.  An M128 x N x K16 MMA from shared memory costs max(32, N / 2) cycles (the A tile is re-read by every
     // MMA), so N <= 64 is as fast per CTA as it gets: layers with fewer tiles than SMs (latency bound) use narrow slices
     // and a deep ring; layers with many tiles use the widest slice that still leaves two stages (fewer CTAs re-reading

@@ -81,6 +81,7 @@ def train(run_name: str, input_dataset_path: str, output_dir: str, *,
     dev = th.device("cuda", th.cuda.current_device())
     # sliding 20-iteration window of [e_tp, e_tn, d_loss, grad_pen | e_gen, g_loss] (train.py:120-127) kept ON the device
     ring = th.zeros(window, 6, device=dev)
+    order_d, order_g = th.tensor([2, 3, 0, 1], device=dev), th.tensor([1, 0], device=dev)      # graph stats -> window columns
     shown = [0.] * 6
     last = [0.] * 6
 
@@ -105,10 +106,10 @@ def train(run_name: str, input_dataset_path: str, output_dir: str, *,
             if graphed is not None:
                 graphed.set_alpha(alpha)
                 d_stats = graphed.critic_step(x_real)            # [d_loss, grad_pen, mean D(real), mean D(fake)]
-                ring[iter_idx % window, :4].copy_(d_stats[[2, 3, 0, 1]])
+                ring[iter_idx % window, :4].copy_(d_stats[order_d])
                 if do_gen:
                     g_stats = graphed.generator_step()           # [g_loss, mean D(fake)]
-                    ring[gen_idx % window, 4:].copy_(g_stats[[1, 0]])
+                    ring[gen_idx % window, 4:].copy_(g_stats[order_g])
             else:
                 z = th.randn(batch_size, rand_channels, height, width, device="cuda")
                 d_loss, gp, out_real, out_fake = train_step.critic_step(gen, disc, None, z, x_real, alpha, step=False)
