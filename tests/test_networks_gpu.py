@@ -316,3 +316,56 @@ def test_repeated_steps_are_bitwise_reproducible():
             continue
         for k, v in snap.items():
             assert torch.equal(v, ref[k]), (rep, k, (v.float() - ref[k].float()).abs().max().item())
+
+
+def test_several_graph_captures_in_one_process():
+    """`train` re-captures at every growth event and bench.py's sweep captures one GraphedSteps per stage: kernel
+    scratch requested during a capture lives in that graph's private memory pool and must die with it (round 2: the
+    process-wide workspace cache handed a destroyed graph's addresses to the next one -> illegal memory access)."""
+    import gc
+    from musicgan_b200.graphed import GraphedSteps
+    batch = 4
+    for stage in (0, 1, 2, 3):
+        gen, disc = build(stage, no.make_state("gen", stage, 41), no.make_state("disc", stage, 42))
+        res = 4 * 2 ** stage
+        og = torch.optim.Adam(gen.parameters(), lr=1e-3, betas=(0.0, 0.9), capturable=True, fused=True)
+        od = torch.optim.Adam(disc.parameters(), lr=1e-3, betas=(0.0, 0.9), capturable=True, fused=True)
+        gs = GraphedSteps(gen, disc, og, od, batch, 32, res, 0.5, warmup=1)
+        x_real = torch.rand(batch, 2, res, res, device="cuda") * 2 - 1
+        for it in range(6):
+            stats = gs.critic_step(x_real)
+            if it % 5 == 0:
+                gs.generator_step()
+        torch.cuda.synchronize()
+        assert torch.isfinite(stats).all()
+        del gs, gen, disc, og, od
+        gc.collect()
+        torch.cuda.empty_cache()
+
+
+def test_one_launch_weight_packing_equals_per_tensor_packing():
+    """ops.prepack (mg_pack_weights_multi: every packed copy of a network in one launch) writes the same bytes as the
+    per-tensor pack kernels the eager path uses, for every kind of copy (bf16 / hi + lo / split parts, both orientations)."""
+    from musicgan_b200.networks import ops
+    stage = 5
+    gen, disc = build(stage, no.make_state("gen", stage, 51), no.make_state("disc", stage, 52))
+    x = (torch.rand(2, 2, 128, 128) * 2 - 1).cuda().requires_grad_(True)
+    z = torch.randn(2, 32, 2, 2).cuda()
+    (disc(gen(z, 0.5), 0.5).mean() + disc.gradient_penalty(x.detach(), gen(z, 0.5).detach(), 0.5)).backward()      # asks for every kind
+    torch.cuda.synchronize()
+    n = 0
+    for module in (gen, disc):
+        single = {(id(p), key): buf.clone() for p in module.parameters() for key, (_, buf) in getattr(p, "_mg_packed", {}).items()}
+        for p in module.parameters():
+            for key, (_, buf) in getattr(p, "_mg_packed", {}).items():
+                buf.zero_()
+        ops.invalidate_pack_cache()
+        ops.prepack(module)
+        torch.cuda.synchronize()
+        for p in module.parameters():
+            for key, (stamp, buf) in getattr(p, "_mg_packed", {}).items():
+                kind, cin, cout = key
+                used = 9 * cin * cout * 2 * ((3 if kind[1] & 2 else 2) if kind[0] == "split" else (2 if kind[1] & 2 else 1))
+                assert torch.equal(buf[:used], single[(id(p), key)][:used]), key
+                n += 1
+    assert n >= 60
