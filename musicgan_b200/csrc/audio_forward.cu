@@ -30,7 +30,7 @@ namespace mg {
 constexpr int kBins = 512;        // n_fft / 2 (Nyquist dropped, functions.py:62)
 constexpr int kHop = 256;
 constexpr int kNfft = 1024;
-constexpr int kFramesPerCta = 32; // k_stft tile
+constexpr int kFramesPerCta = 16; // k_stft tile (16 frames: 69 KB of shared memory -> three CTAs per SM)
 constexpr int kStftWarps = 8;
 constexpr int kSeg = 64;          // frames per unwrap segment
 
@@ -78,7 +78,7 @@ struct StftSmem {
 enum { STFT_POLAR = 0, STFT_COMPLEX = 1 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kStftWarps * 32, 2)
+__global__ void __launch_bounds__(kStftWarps * 32, 3)
 k_stft(const float* __restrict__ wav, int64_t n_samples, int channels, int64_t clip_stride, int64_t n_frames,
        const float* __restrict__ window, const float* __restrict__ bark_gain, const DeviceTables* __restrict__ tables,
        float* __restrict__ out_a,      // POLAR: phi [clip][t][512]      COMPLEX: c64 [clip][t][512]
