@@ -154,7 +154,7 @@ struct IstftSmem {
 };
 
 // grid (ceil(n_hops / (8*16)), n_clips), block 256
-__global__ void __launch_bounds__(kIstftWarps * 32, 2)
+__global__ void __launch_bounds__(kIstftWarps * 32, 3)
 k_istft(const float2* __restrict__ X, int64_t Wt, const float* __restrict__ window,
         const DeviceTables* __restrict__ tables, const int* __restrict__ keys, float* __restrict__ wav) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
