@@ -160,12 +160,13 @@ int mg_pack_job_fill(mgPackJob* job_host, const float* w_f32, void* packed, int 
 int mg_pack_weights_multi(const mgPackJob* jobs_dev, int n_jobs, int max_total, mgStream stream);
 
 /* Weight gradient of the same convolution: dw[co][ci][ky][kx] = sum_{b,y,x} dy[b][y][x][co] *
- * xin[b][y+ky-1][x+kx-1][ci]   (xin = x, or x read through a nearest x2 upsampling when upsample_in != 0).
- * dy [B][H][W][Cout] bf16, x [B][H(/2)][W(/2)][Cin] bf16, dw fp32 [Cout][Cin][3][3] OVERWRITTEN (deterministic
- * two-stage reduction through `ws`, >= mg_conv3x3_wgrad_workspace_bytes). */
+ * xin[b][y+ky-1][x+kx-1][ci]   (xin = x, or x read through a nearest x2 upsampling when flags bit 0 is set).
+ * dy [B][H][W][Cout] bf16, x [B][H(/2)][W(/2)][Cin] bf16, dw fp32 [Cout][Cin][3][3] OVERWRITTEN -- or, with flags
+ * bit 1, ADDED TO (a further contribution to the same parameter's gradient) -- by a deterministic two-stage reduction
+ * through `ws` (>= mg_conv3x3_wgrad_workspace_bytes). */
 size_t mg_conv3x3_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout);
 int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, void* ws, size_t ws_bytes,
-                          int B, int H, int W, int Cin, int Cout, int upsample_in, mgStream stream);
+                          int B, int H, int W, int Cin, int Cout, int flags, mgStream stream);
 
 /* ------------------------------------------------------------------------------------------
  * Memory-bound layers around the convolutions (pointwise.cu).  "mask" = LeakyReLU(0.2) derivative taken

@@ -156,7 +156,7 @@ def run(args, rank, world, local, timed_region, ClockSampler, peaks):
     hbm_bound = t_hbm >= t_tensor
     step_tf = batch * flop_per_iter(stage) * args.steps / (ms * 1e-3) / 1e12
     cpu = cpu_baseline(batch, stage=stage, budget_s=args.cpu_seconds * 2)
-    torch_arm = torch_b200_numbers(stage, batch) if world == 1 else None
+    torch_arm = torch_b200_numbers(stage, batch) if world == 1 and not os.environ.get("MG_BENCH_NO_TORCH") else None
     return {
         "metric": "GAN train steps/s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -302,7 +302,7 @@ k_conv3x3_wgrad(const WgradParams p) {
 // dw[co][ci][tap] = sum over the gx CTAs of a group of part[cta][group][j][L][co], rows r = tap*Cin + ci = (g*nb + j)*128 + L
 // block = 8 warps x 32 consecutive outputs (consecutive co -> 128-byte rows); warp w sums CTAs w, w+8, ...; smem combine
 __global__ void __launch_bounds__(256)
-k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dw, int Cin, int Cout, int gx, int groups, int nb, FastDiv div_cin) {
+k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dw, int Cin, int Cout, int gx, int groups, int nb, FastDiv div_cin, int accumulate) {
     __shared__ float red[8][33];
     pdl_trigger();
     pdl_wait();
@@ -328,7 +328,8 @@ k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dw, int Cin, 
 #pragma unroll
         for (int k = 0; k < 8; ++k) s += red[k][lane];
         const int tap = fast_div(r, div_cin), ci = r - tap * Cin;
-        dw[((size_t)co * Cin + ci) * 9 + tap] = s;
+        float* dst = dw + ((size_t)co * Cin + ci) * 9 + tap;
+        *dst = accumulate ? *dst + s : s;      // accumulate: a further contribution to the same parameter (ops.WgradLane)
     }
 }
 
@@ -360,7 +361,8 @@ extern "C" size_t mg_conv3x3_wgrad_workspace_bytes(int B, int H, int W, int Cin,
 }
 
 extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, void* ws, size_t ws_bytes,
-                                     int B, int H, int W, int Cin, int Cout, int upsample_in, mgStream stream) {
+                                     int B, int H, int W, int Cin, int Cout, int flags, mgStream stream) {
+    const int upsample_in = flags & 1, accumulate = (flags >> 1) & 1;
     if (!dy || !x || !dw || !ws) return MG_ERR_BAD_ARG;
     if (ws_bytes < mg_conv3x3_wgrad_workspace_bytes(B, H, W, Cin, Cout)) return MG_ERR_WORKSPACE;
     if (((uintptr_t)ws & 15) != 0) return MG_ERR_BAD_ARG;
@@ -408,7 +410,7 @@ extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, v
     {
         ProfScope ps("k_wgrad_reduce", st);
         const int total = 9 * Cin * Cout;
-        launch_pdl(k_wgrad_reduce, dim3((total + 31) / 32), dim3(256), 0, st, (const float*)ws, dw, Cin, Cout, gx, groups, nb, p.div_cin);
+        launch_pdl(k_wgrad_reduce, dim3((total + 31) / 32), dim3(256), 0, st, (const float*)ws, dw, Cin, Cout, gx, groups, nb, p.div_cin, accumulate);
     }
     return check_launch("k_conv3x3_wgrad");
 }

@@ -49,6 +49,7 @@ class GraphedSteps:
         if two_streams is None:
             two_streams = os.environ.get("MG_TWO_STREAMS", "1") != "0"
         self._branch = th.cuda.Stream(device=dev) if two_streams else None
+        self._wgrad_lanes = os.environ.get("MG_WGRAD_LANES", "1") != "0"
         if two_streams and hasattr(th.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
             # the parameters' AccumulateGrad nodes were created on another stream; gradients are collected by
             # autograd.grad (never accumulated), so the mismatch the engine warns about is intended
@@ -76,19 +77,21 @@ class GraphedSteps:
             x_fake = gen(z, alpha)
         params = [p for p in disc.parameters()]
         if self._branch is None:
-            out = disc(th.cat([self.x_real, x_fake], dim=0), alpha)
-            d_loss = networks.wasserstein_discriminator_loss(out[:n], out[n:])
-            gp = disc.gradient_penalty(self.x_real, x_fake, alpha, eps=self.eps)
-            grads = th.autograd.grad(d_loss + gp, params, allow_unused=True)
+            with self._lane(params) as lane:
+                out = disc(th.cat([self.x_real, x_fake], dim=0), alpha)
+                d_loss = networks.wasserstein_discriminator_loss(out[:n], out[n:])
+                gp = disc.gradient_penalty(self.x_real, x_fake, alpha, eps=self.eps)
+                grads = lane.merge(th.autograd.grad(d_loss + gp, params, allow_unused=True))
         else:
             main, branch = th.cuda.current_stream(), self._branch
             branch.wait_stream(main)
-            with th.cuda.stream(branch):
+            with th.cuda.stream(branch), self._lane(params) as lane:
                 gp = disc.gradient_penalty(self.x_real, x_fake, alpha, eps=self.eps)
-                grads_gp = th.autograd.grad(gp, params, allow_unused=True)
-            out = disc(th.cat([self.x_real, x_fake], dim=0), alpha)
-            d_loss = networks.wasserstein_discriminator_loss(out[:n], out[n:])
-            grads_w = th.autograd.grad(d_loss, params, allow_unused=True)
+                grads_gp = lane.merge(th.autograd.grad(gp, params, allow_unused=True))
+            with self._lane(params) as lane:
+                out = disc(th.cat([self.x_real, x_fake], dim=0), alpha)
+                d_loss = networks.wasserstein_discriminator_loss(out[:n], out[n:])
+                grads_w = lane.merge(th.autograd.grad(d_loss, params, allow_unused=True))
             main.wait_stream(branch)
             # sum of the two branches' gradients: one multi-tensor add instead of one tiny kernel per parameter
             both = [(gw, gg) for gw, gg in zip(grads_w, grads_gp) if gw is not None and gg is not None]
@@ -107,13 +110,17 @@ class GraphedSteps:
         params = [p for p in gen.parameters()]
         ops.prepack(gen)
         ops.prepack(disc)
-        with frozen(disc):
+        with frozen(disc), self._lane(params) as lane:
             out_fake = disc(gen(z, alpha), alpha)
             g_loss = networks.wasserstein_generator_loss(out_fake)
-            grads = th.autograd.grad(g_loss, params, allow_unused=True)
+            grads = lane.merge(th.autograd.grad(g_loss, params, allow_unused=True))
         self._install(params, grads, self.bucket_g)
         self.og.step()
         return th.stack([g_loss.detach(), out_fake.mean().detach()])
+
+    def _lane(self, params):
+        # weight gradients on a second stream beside the data-gradient chain (ops.WgradLane); depth 0 = in line
+        return ops.WgradLane(params if self._wgrad_lanes else [])
 
     @staticmethod
     def _install(params, grads, bucket):

@@ -53,6 +53,18 @@ class input_grads_only:
         return False
 
 
+def _wgrad(w, g, x, upsample_in: bool = False):
+    """Weight gradient of a block: handed to the step's weight-gradient lane when one is open and takes this parameter
+    (ops.WgradLane: computed on a second stream, collected by the step; autograd sees None), else computed in line."""
+    lane = ops.wgrad_lane()
+    if lane is not None and lane.accepts(w):
+        lane.submit(w, g, x, upsample_in)
+        return None
+    if upsample_in:
+        return ops.conv3x3_wgrad(g, x, upsample_in=True)
+    return ConvWgrad.apply(g, x)
+
+
 class ConvFprop(Function):
     """y = conv3x3(x, w), no bias / activation (linear in x and in w)."""
 
@@ -65,7 +77,7 @@ class ConvFprop(Function):
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         gx = ConvDgrad.apply(gy, w) if ctx.needs_input_grad[0] else None
-        gw = ConvWgrad.apply(gy, x) if ctx.needs_input_grad[1] and _param_grads[0] else None
+        gw = _wgrad(w, gy, x) if ctx.needs_input_grad[1] and _param_grads[0] else None
         return gx, gw
 
 
@@ -81,7 +93,7 @@ class ConvDgrad(Function):
     def backward(ctx, gdx):
         g, w = ctx.saved_tensors
         gg = ConvFprop.apply(gdx, w) if ctx.needs_input_grad[0] else None
-        gw = ConvWgrad.apply(g, gdx) if ctx.needs_input_grad[1] and _param_grads[0] else None
+        gw = _wgrad(w, g, gdx) if ctx.needs_input_grad[1] and _param_grads[0] else None
         return gg, gw
 
 
@@ -127,7 +139,7 @@ class ConvBiasLReLU(Function):
         else:
             gz, gb = LReLUBwd.apply(gy, y, ctx.needs_input_grad[2] and _param_grads[0])
         gx = ConvDgrad.apply(gz, w) if ctx.needs_input_grad[0] else None
-        gw = ConvWgrad.apply(gz, x) if ctx.needs_input_grad[1] and _param_grads[0] else None
+        gw = _wgrad(w, gz, x) if ctx.needs_input_grad[1] and _param_grads[0] else None
         return gx, gw, (gb if ctx.needs_input_grad[2] else None)
 
 
@@ -194,7 +206,7 @@ class ConvBiasLReLUPool(Function):
         x, w, h = ctx.saved_tensors
         gz, gb = UnpoolLReLUBwd.apply(gp, h, ctx.needs_input_grad[2] and _param_grads[0])
         gx = ConvDgrad.apply(gz, w) if ctx.needs_input_grad[0] else None
-        gw = ConvWgrad.apply(gz, x) if ctx.needs_input_grad[1] and _param_grads[0] else None
+        gw = _wgrad(w, gz, x) if ctx.needs_input_grad[1] and _param_grads[0] else None
         return gx, gw, (gb if ctx.needs_input_grad[2] else None)
 
 
@@ -235,7 +247,7 @@ class GenConv(Function):
             if ctx.upsample_in:      # backward of the nearest upsampling folded into the read: sum of each 2x2 block
                 gx = ops.pool2(gx, sum_pool=True)
         if ctx.needs_input_grad[1]:
-            gw = ops.conv3x3_wgrad(gz, xa, upsample_in=ctx.upsample_in)
+            gw = _wgrad(w, gz, xa, ctx.upsample_in)
         return gx, gw, gb, None
 
 

@@ -5,6 +5,7 @@ memory -- exactly what the kernels read and write.  Weights are the fp32 master 
 (Cout, Cin, 3, 3) of the drop-in nn.Modules (same shapes as the reference's nn.Conv2d)."""
 from __future__ import annotations
 
+import collections
 import ctypes
 import os
 from ctypes import c_int, c_size_t, c_void_p
@@ -314,24 +315,107 @@ def conv3x3(x: th.Tensor, w: th.Tensor, bias=None, *, lrelu=False, pixelnorm=Fal
     return (y, inv) if want_inv_norm else y
 
 
-def conv3x3_wgrad(dy: th.Tensor, x: th.Tensor, *, upsample_in=False) -> th.Tensor:
+def conv3x3_wgrad(dy: th.Tensor, x: th.Tensor, *, upsample_in=False, out=None, accumulate=False) -> th.Tensor:
     """dw[co][ci][ky][kx] = sum_{b,y,x} dy[b,co,y,x] * xin[b,ci,y+ky-1,x+kx-1]  (fp32), xin = x or its nearest
-    x2 upsampling."""
+    x2 upsampling.  `out`: write into (or, with `accumulate`, add to) an existing (Cout, Cin, 3, 3) fp32 tensor."""
     # terminal product (nothing propagates from it): bf16 operands are enough, also for the fp32 layers of the precise path
     dy, x = as_act(dy), as_act(x)
     _check_act(dy, "wgrad dy"); _check_act(x, "wgrad x")
     B, cout, H, W = dy.shape
     cin = x.shape[1]
     assert x.shape[0] == B and (x.shape[2] * (2 if upsample_in else 1), x.shape[3] * (2 if upsample_in else 1)) == (H, W)
-    dw = th.empty((cout, cin, 3, 3), dtype=th.float32, device=dy.device)      # overwritten: no zero fill needed
+    if out is None:
+        assert not accumulate
+        dw = th.empty((cout, cin, 3, 3), dtype=th.float32, device=dy.device)      # overwritten: no zero fill needed
+    else:
+        dw = out
+        assert dw.shape == (cout, cin, 3, 3) and dw.dtype == th.float32 and dw.is_contiguous() and dw.device == dy.device
     l = _l()
     _account(2.0 * B * H * W * 9 * cin * cout, 2.0 * (x.numel() + dy.numel()))
     ws = _workspace(dy.device, l.mg_conv3x3_wgrad_workspace_bytes(B, H, W, cin, cout), "wgrad")
     with th.cuda.device(dy.device):
         _lib.check(l.mg_conv3x3_wgrad_bf16(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(),
-                                           B, H, W, cin, cout, 1 if upsample_in else 0,
+                                           B, H, W, cin, cout, (1 if upsample_in else 0) | (2 if accumulate else 0),
                                            th.cuda.current_stream().cuda_stream), "mg_conv3x3_wgrad_bf16")
     return dw
+
+
+# Weight gradients are LEAVES of the backward pass: nothing downstream waits for them until the optimiser step, yet
+# issued in line they sit on the serial chain of a step (54 launches of a critic step, 16-25 us each on the
+# low-resolution layers whatever their size, plus their reduce kernels and operand casts).  Inside a `WgradLane` the
+# convolution blocks hand them to a second stream instead: the lane waits for the gradient it consumes, runs cast ->
+# k_conv3x3_wgrad -> k_wgrad_reduce there, and writes (first contribution) or adds (further ones, e.g. the two
+# appearances of a critic weight in the penalty's double backward) into one fp32 tensor per parameter.  The step joins
+# the lane once, before the optimiser.  Under CUDA-graph capture the waits become graph edges, so the replayed graph
+# runs the weight-gradient chain beside the data-gradient chain.
+_lane = [None]
+_lane_streams = {}
+
+
+class WgradLane:
+    def __init__(self, params, depth: int = None):
+        self.params = list(params)
+        self.index = {p.data_ptr(): i for i, p in enumerate(self.params)
+                      if p.requires_grad and p.dim() == 4 and tuple(p.shape[2:]) == (3, 3) and p.shape[0] >= 16 and p.shape[1] >= 16}
+        self.out = {}
+        self.depth = int(os.environ.get("MG_WGRAD_LANE_DEPTH", "6")) if depth is None else depth
+        self.pending = collections.deque()
+        self.origin = None
+        self.stream = None
+
+    def __enter__(self):
+        self.origin = th.cuda.current_stream()
+        key = (self.origin.device.index, self.origin.cuda_stream)
+        s = _lane_streams.get(key)
+        if s is None:
+            s = _lane_streams[key] = th.cuda.Stream(device=self.origin.device)
+        self.stream = s
+        self.prev, _lane[0] = _lane[0], self
+        return self
+
+    def __exit__(self, *exc):
+        _lane[0] = self.prev
+        self.join()
+        return False
+
+    def accepts(self, w: th.Tensor) -> bool:
+        # only first-order work (no graph is being recorded through this product) issued from the lane's own stream
+        return (not th.is_grad_enabled()) and w.data_ptr() in self.index and th.cuda.current_stream() == self.origin
+
+    def submit(self, w: th.Tensor, g: th.Tensor, x: th.Tensor, upsample_in: bool = False) -> None:
+        cur = self.origin
+        i = self.index[w.data_ptr()]
+        first = i not in self.out
+        if first:
+            self.out[i] = th.empty(tuple(w.shape), dtype=th.float32, device=w.device)
+        self.stream.wait_stream(cur)
+        with th.cuda.stream(self.stream):
+            conv3x3_wgrad(g, x, upsample_in=upsample_in, out=self.out[i], accumulate=not first)
+            ev = th.cuda.Event()
+            ev.record(self.stream)
+        # g and x were allocated on the origin stream: they stay referenced until that stream has waited for the lane
+        # (its allocator may then hand their memory to later kernels of the origin stream)
+        self.pending.append((ev, g, x))
+        while len(self.pending) > self.depth:
+            cur.wait_event(self.pending.popleft()[0])
+
+    def join(self) -> None:
+        if self.stream is not None and (self.pending or self.out):
+            self.origin.wait_stream(self.stream)
+        self.pending.clear()
+
+    def merge(self, grads):
+        """`grads` of autograd.grad(..., self.params, allow_unused=True) with the lane's weight gradients filled in."""
+        self.join()
+        merged = []
+        for i, g in enumerate(grads):
+            mine = self.out.get(i)
+            merged.append(mine if g is None else (g if mine is None else g + mine))
+        return merged
+
+
+def wgrad_lane():
+    return _lane[0]
 
 
 def _stream():
