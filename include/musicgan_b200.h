@@ -167,6 +167,10 @@ int mg_pack_weights_multi(const mgPackJob* jobs_dev, int n_jobs, int max_total, 
 size_t mg_conv3x3_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout);
 int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, void* ws, size_t ws_bytes,
                           int B, int H, int W, int Cin, int Cout, int flags, mgStream stream);
+/* The same launch also producing the BIAS gradient db[co] = sum_{b,y,x} dy[b][y][x][co] (fp32 [Cout]) as one more row of
+ * the GEMM (an operand row of ones): no separate column-sum pass over dy.  flags bit 2: add to db instead of overwriting. */
+int mg_conv3x3_wgrad_bias_bf16(const void* dy, const void* x, float* dw, float* db, void* ws, size_t ws_bytes,
+                               int B, int H, int W, int Cin, int Cout, int flags, mgStream stream);
 
 /* ------------------------------------------------------------------------------------------
  * Memory-bound layers around the convolutions (pointwise.cu).  "mask" = LeakyReLU(0.2) derivative taken

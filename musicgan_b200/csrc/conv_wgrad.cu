@@ -44,6 +44,7 @@ struct WgradParams {
     int tiles_per_img;
     FastDiv div_img, div_tx;
     int ablate;                 // debug (MG_WGRAD_ABLATE): 1 no copies, 2 no MMAs, 4 no operand staging (ldmatrix / tcgen05.st)
+    int bias_row;               // 9 * Cin: an A row of ones whose products are the bias gradient sum_pixels dy[.][co]; -1 = none
 };
 
 __global__ void __launch_bounds__(kWgradThreads, 1)
@@ -241,6 +242,22 @@ k_conv3x3_wgrad(const WgradParams p) {
                 }
             }
         }
+        // Bias gradient: row 9 * Cin of the A operand is a row of ones, so D[9 * Cin][co] = sum over the pixels of dy[.][co]
+        // (dy is zero outside the image).  9 * Cin is a multiple of 16: the row opens a 16-row group that no tile writes
+        // (goff < 0), so it is written ONCE here into both A buffers; its neighbours in the lane quarter get zeros (the
+        // valid ones are rewritten for every tile, the others only feed accumulator rows that nobody reads).
+        if (p.bias_row >= 0) {
+            const int jb = (p.bias_row >> 7) - blk0;
+            if (jb >= 0 && jb < nb && ((p.bias_row & 127) >> 5) == quarter) {
+                uint32_t r[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) r[k] = L == (p.bias_row & 127) ? 0x3F803F80u : 0u;
+                for (int b2 = 0; b2 < 2; ++b2)
+                    for (int c = 0; c < 4; ++c)
+                        tmem_st8(tmem_a + b2 * a_cols + jb * 64 + khalf * 32 + c * 8 + lane_addr, r);
+                tmem_wait_st();
+            }
+        }
         int slot = 0, buf = 0; uint32_t ph = 0, aph = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             mbar_wait(&a_empty[buf], aph ^ 1u);
@@ -299,20 +316,22 @@ k_conv3x3_wgrad(const WgradParams p) {
     if (warp == kMma0) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-// dw[co][ci][tap] = sum over the gx CTAs of a group of part[cta][group][j][L][co], rows r = tap*Cin + ci = (g*nb + j)*128 + L
+// dw[co][ci][tap] = sum over the gx CTAs of a group of part[cta][group][j][L][co], rows r = tap*Cin + ci = (g*nb + j)*128 + L;
+// with `db` the row r = 9 * Cin holds the bias gradient.  accumulate: bit 0 add to dw, bit 1 add to db (else overwrite).
 // block = 8 warps x 32 consecutive outputs (consecutive co -> 128-byte rows); warp w sums CTAs w, w+8, ...; smem combine
 __global__ void __launch_bounds__(256)
-k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dw, int Cin, int Cout, int gx, int groups, int nb, FastDiv div_cin, int accumulate) {
+k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dw, float* __restrict__ db, int Cin, int Cout, int gx, int groups, int nb,
+               FastDiv div_cin, int accumulate) {
     __shared__ float red[8][33];
     pdl_trigger();
     pdl_wait();
-    const int total = 9 * Cin * Cout;
+    const int total = 9 * Cin * Cout, total_all = total + (db ? Cout : 0);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int t = blockIdx.x * 32 + lane;
     float s0 = 0.f, s1 = 0.f;
     int r = 0, co = 0;
-    if (t < total) {
-        r = t / Cout; co = t - r * Cout;
+    if (t < total_all) {
+        if (t < total) { r = t / Cout; co = t - r * Cout; } else { r = 9 * Cin; co = t - total; }
         const int blk = r >> 7, L = r & 127;
         const int g = blk / nb, j = blk - g * nb;
         const float* src = part + (((size_t)g * nb + j) * 128 + L) * Cout + co;
@@ -323,13 +342,17 @@ k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dw, int Cin, 
     }
     red[w][lane] = s0 + s1;
     __syncthreads();
-    if (w == 0 && t < total) {
+    if (w == 0 && t < total_all) {
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) s += red[k][lane];
-        const int tap = fast_div(r, div_cin), ci = r - tap * Cin;
-        float* dst = dw + ((size_t)co * Cin + ci) * 9 + tap;
-        *dst = accumulate ? *dst + s : s;      // accumulate: a further contribution to the same parameter (ops.WgradLane)
+        if (t < total) {
+            const int tap = fast_div(r, div_cin), ci = r - tap * Cin;
+            float* dst = dw + ((size_t)co * Cin + ci) * 9 + tap;
+            *dst = (accumulate & 1) ? *dst + s : s;      // a further contribution to the same parameter (ops.WgradLane)
+        } else {
+            db[co] = (accumulate & 2) ? db[co] + s : s;
+        }
     }
 }
 
@@ -337,9 +360,9 @@ k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dw, int Cin, 
 
 using namespace mg;
 
-static void wgrad_grid(int n_tiles, int Cin, int Cout, int* nb_out, int* groups_out, int* gx_out) {
+static void wgrad_grid(int n_tiles, int Cin, int Cout, int with_bias, int* nb_out, int* groups_out, int* gx_out) {
     const int sm_count = current_sm_count();
-    const int n_blocks = (9 * Cin + 127) / 128;
+    const int n_blocks = (9 * Cin + (with_bias ? 1 : 0) + 127) / 128;
     int nb = 512 / (Cout + 128); nb = nb > kMaxBlocks ? kMaxBlocks : (nb < 1 ? 1 : nb);
     nb = nb > n_blocks ? n_blocks : nb;
     while (nb > 1 && n_tiles * ((n_blocks + nb - 1) / nb) < sm_count) --nb;
@@ -355,14 +378,19 @@ static void wgrad_grid(int n_tiles, int Cin, int Cout, int* nb_out, int* groups_
 extern "C" size_t mg_conv3x3_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout) {
     if (B <= 0 || H <= 0 || W <= 0 || Cin < 16 || Cout < 16) return 0;
     const int n_tiles = B * ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
-    int nb, groups, gx;
-    wgrad_grid(n_tiles, Cin, Cout, &nb, &groups, &gx);
-    return align_up((size_t)gx * groups * nb * 128 * Cout * sizeof(float), 256);
+    size_t need = 0;
+    for (int with_bias = 0; with_bias < 2; ++with_bias) {      // one size for both entry points
+        int nb, groups, gx;
+        wgrad_grid(n_tiles, Cin, Cout, with_bias, &nb, &groups, &gx);
+        const size_t n = (size_t)gx * groups * nb * 128 * Cout * sizeof(float);
+        need = n > need ? n : need;
+    }
+    return align_up(need, 256);
 }
 
-extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, void* ws, size_t ws_bytes,
-                                     int B, int H, int W, int Cin, int Cout, int flags, mgStream stream) {
-    const int upsample_in = flags & 1, accumulate = (flags >> 1) & 1;
+extern "C" int mg_conv3x3_wgrad_bias_bf16(const void* dy, const void* x, float* dw, float* db, void* ws, size_t ws_bytes,
+                                          int B, int H, int W, int Cin, int Cout, int flags, mgStream stream) {
+    const int upsample_in = flags & 1, accumulate = (flags >> 1) & 3;
     if (!dy || !x || !dw || !ws) return MG_ERR_BAD_ARG;
     if (ws_bytes < mg_conv3x3_wgrad_workspace_bytes(B, H, W, Cin, Cout)) return MG_ERR_WORKSPACE;
     if (((uintptr_t)ws & 15) != 0) return MG_ERR_BAD_ARG;
@@ -376,9 +404,10 @@ extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, v
     // Row blocks: rows r = tap * Cin + ci in blocks of 128.  A CTA keeps nb * Cout accumulator columns plus two A buffers
     // of nb * 64 columns in its 512 TMEM columns; more blocks than fit are split over blockIdx.y (each group re-reads
     // the tiles).  When there are few tiles the blocks are spread over more CTAs anyway (small-spatial layers).
-    p.n_blocks = (9 * Cin + 127) / 128;
+    p.bias_row = db ? 9 * Cin : -1;
+    p.n_blocks = (9 * Cin + (db ? 1 : 0) + 127) / 128;
     int nb, groups, gx;
-    wgrad_grid(p.n_tiles, Cin, Cout, &nb, &groups, &gx);
+    wgrad_grid(p.n_tiles, Cin, Cout, db ? 1 : 0, &nb, &groups, &gx);
     p.blocks_per_cta = nb;
     int cols = 32; while (cols < nb * (Cout + 128)) cols <<= 1;
     p.tmem_cols = cols;
@@ -409,8 +438,13 @@ extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, v
     }
     {
         ProfScope ps("k_wgrad_reduce", st);
-        const int total = 9 * Cin * Cout;
-        launch_pdl(k_wgrad_reduce, dim3((total + 31) / 32), dim3(256), 0, st, (const float*)ws, dw, Cin, Cout, gx, groups, nb, p.div_cin, accumulate);
+        const int total = 9 * Cin * Cout + (db ? Cout : 0);
+        launch_pdl(k_wgrad_reduce, dim3((total + 31) / 32), dim3(256), 0, st, (const float*)ws, dw, db, Cin, Cout, gx, groups, nb, p.div_cin, accumulate);
     }
     return check_launch("k_conv3x3_wgrad");
+}
+
+extern "C" int mg_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, void* ws, size_t ws_bytes,
+                                     int B, int H, int W, int Cin, int Cout, int flags, mgStream stream) {
+    return mg_conv3x3_wgrad_bias_bf16(dy, x, dw, nullptr, ws, ws_bytes, B, H, W, Cin, Cout, flags & 3, stream);
 }

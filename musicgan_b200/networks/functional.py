@@ -53,13 +53,24 @@ class input_grads_only:
         return False
 
 
-def _wgrad(w, g, x, upsample_in: bool = False):
+def _lane_bias(w, b, act: th.Tensor) -> bool:
+    """True if the open weight-gradient lane will also produce this convolution's bias gradient (from the same launch:
+    no column sums in the LeakyReLU / PixelNorm backward kernel, no reduce launch).  Only on the bf16 layers: there the
+    launch sums exactly the values the column-sum kernel would; on the fp32 layers of the precise path it would sum
+    their bf16 roundings (measured: the critic's bias updates then differ by 2e-3 from the eager step's)."""
+    lane = ops.wgrad_lane()
+    return lane is not None and act.dtype == th.bfloat16 and lane.accepts_bias(w, b)
+
+
+def _wgrad(w, g, x, upsample_in: bool = False, bias=None):
     """Weight gradient of a block: handed to the step's weight-gradient lane when one is open and takes this parameter
-    (ops.WgradLane: computed on a second stream, collected by the step; autograd sees None), else computed in line."""
+    (ops.WgradLane: computed on a second stream, collected by the step; autograd sees None), else computed in line.
+    `bias`: only after _lane_bias(w, bias) said yes."""
     lane = ops.wgrad_lane()
     if lane is not None and lane.accepts(w):
-        lane.submit(w, g, x, upsample_in)
+        lane.submit(w, g, x, upsample_in, bias=bias)
         return None
+    assert bias is None
     if upsample_in:
         return ops.conv3x3_wgrad(g, x, upsample_in=True)
     return ConvWgrad.apply(g, x)
@@ -127,20 +138,24 @@ class ConvBiasLReLU(Function):
     @staticmethod
     def forward(ctx, x, w, b):
         y = ops.conv3x3(_act(x), w.float().contiguous(), b.float().contiguous(), lrelu=True, split_w=True, exact_w=True)
-        ctx.save_for_backward(x, w, y)
+        ctx.save_for_backward(x, w, y, b)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, w, y = ctx.saved_tensors
+        x, w, y, b = ctx.saved_tensors
+        want_gw = ctx.needs_input_grad[1] and _param_grads[0]
+        want_gb = ctx.needs_input_grad[2] and _param_grads[0]
+        lane_b = want_gw and want_gb and _lane_bias(w, b, y)
         if _UNFUSED_LRELU_BWD:
             gz = gy * _lrelu_mask(y)
             gb = gz.float().sum(dim=(0, 2, 3))
+            lane_b = False
         else:
-            gz, gb = LReLUBwd.apply(gy, y, ctx.needs_input_grad[2] and _param_grads[0])
+            gz, gb = LReLUBwd.apply(gy, y, want_gb and not lane_b)
         gx = ConvDgrad.apply(gz, w) if ctx.needs_input_grad[0] else None
-        gw = _wgrad(w, gz, x) if ctx.needs_input_grad[1] and _param_grads[0] else None
-        return gx, gw, (gb if ctx.needs_input_grad[2] else None)
+        gw = _wgrad(w, gz, x, bias=b if lane_b else None) if want_gw else None
+        return gx, gw, (gb if ctx.needs_input_grad[2] and not lane_b else None)
 
 
 class LReLUBwd(Function):
@@ -198,16 +213,19 @@ class ConvBiasLReLUPool(Function):
     @staticmethod
     def forward(ctx, x, w, b):
         h = ops.conv3x3(_act(x), w.float().contiguous(), b.float().contiguous(), lrelu=True, split_w=True, exact_w=True)
-        ctx.save_for_backward(x, w, h)
+        ctx.save_for_backward(x, w, h, b)
         return ops.pool2(h)
 
     @staticmethod
     def backward(ctx, gp):
-        x, w, h = ctx.saved_tensors
-        gz, gb = UnpoolLReLUBwd.apply(gp, h, ctx.needs_input_grad[2] and _param_grads[0])
+        x, w, h, b = ctx.saved_tensors
+        want_gw = ctx.needs_input_grad[1] and _param_grads[0]
+        want_gb = ctx.needs_input_grad[2] and _param_grads[0]
+        lane_b = want_gw and want_gb and _lane_bias(w, b, h)
+        gz, gb = UnpoolLReLUBwd.apply(gp, h, want_gb and not lane_b)
         gx = ConvDgrad.apply(gz, w) if ctx.needs_input_grad[0] else None
-        gw = _wgrad(w, gz, x) if ctx.needs_input_grad[1] and _param_grads[0] else None
-        return gx, gw, (gb if ctx.needs_input_grad[2] else None)
+        gw = _wgrad(w, gz, x, bias=b if lane_b else None) if want_gw else None
+        return gx, gw, (gb if ctx.needs_input_grad[2] and not lane_b else None)
 
 
 class GenConv(Function):
@@ -229,17 +247,18 @@ class GenConv(Function):
             t = ops.conv3x3(xa, wf, bf, lrelu=True, upsample_in=upsample_in, split_w=True).float()
             inv = th.rsqrt(t.pow(2).mean(dim=1) + PN_EPS)
             o = ops.as_act(t * inv[:, None], xa.dtype)
-        ctx.save_for_backward(xa, w, o, inv)
+        ctx.save_for_backward(xa, w, o, inv, b)
         ctx.upsample_in = upsample_in
         return o
 
     @staticmethod
     @th.autograd.function.once_differentiable
     def backward(ctx, go):
-        xa, w, o, inv = ctx.saved_tensors
+        xa, w, o, inv, b = ctx.saved_tensors
         # PixelNorm + LeakyReLU backward and the bias gradient in one kernel:
         #   g_t = (g_o - o * mean_c(g_o * o)) / n ;  g_z = g_t * mask(o) ;  g_b = sum_pixels g_z
-        gz, gb = ops.pixelnorm_lrelu_bwd(go, o, inv, want_bias_grad=ctx.needs_input_grad[2])
+        lane_b = ctx.needs_input_grad[1] and ctx.needs_input_grad[2] and _lane_bias(w, b, o)
+        gz, gb = ops.pixelnorm_lrelu_bwd(go, o, inv, want_bias_grad=ctx.needs_input_grad[2] and not lane_b)
         gx = gw = None
         wf = w.float().contiguous()
         if ctx.needs_input_grad[0]:
@@ -247,7 +266,7 @@ class GenConv(Function):
             if ctx.upsample_in:      # backward of the nearest upsampling folded into the read: sum of each 2x2 block
                 gx = ops.pool2(gx, sum_pool=True)
         if ctx.needs_input_grad[1]:
-            gw = _wgrad(w, gz, xa, ctx.upsample_in)
+            gw = _wgrad(w, gz, xa, ctx.upsample_in, bias=b if lane_b else None)
         return gx, gw, gb, None
 
 

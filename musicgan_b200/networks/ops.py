@@ -83,6 +83,8 @@ def _l():
             l.mg_conv3x3_wgrad_workspace_bytes.argtypes = [c_int] * 5
             l.mg_conv3x3_wgrad_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                                 c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
+            l.mg_conv3x3_wgrad_bias_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                                     c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
         c_int64 = ctypes.c_int64
         l.mg_rgb_expand_bf16.argtypes = [c_void_p] * 5 + [c_int, c_int64, c_int, c_int, c_void_p]
         l.mg_rgb_project_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]
@@ -315,9 +317,12 @@ def conv3x3(x: th.Tensor, w: th.Tensor, bias=None, *, lrelu=False, pixelnorm=Fal
     return (y, inv) if want_inv_norm else y
 
 
-def conv3x3_wgrad(dy: th.Tensor, x: th.Tensor, *, upsample_in=False, out=None, accumulate=False) -> th.Tensor:
+def conv3x3_wgrad(dy: th.Tensor, x: th.Tensor, *, upsample_in=False, out=None, accumulate=False, bias_out=None,
+                  accumulate_bias=False) -> th.Tensor:
     """dw[co][ci][ky][kx] = sum_{b,y,x} dy[b,co,y,x] * xin[b,ci,y+ky-1,x+kx-1]  (fp32), xin = x or its nearest
-    x2 upsampling.  `out`: write into (or, with `accumulate`, add to) an existing (Cout, Cin, 3, 3) fp32 tensor."""
+    x2 upsampling.  `out`: write into (or, with `accumulate`, add to) an existing (Cout, Cin, 3, 3) fp32 tensor.
+    `bias_out` (Cout,) fp32: also the bias gradient sum_{b,y,x} dy[b,co,y,x], from the same launch (a row of ones in the
+    GEMM), written or -- `accumulate_bias` -- added."""
     # terminal product (nothing propagates from it): bf16 operands are enough, also for the fp32 layers of the precise path
     dy, x = as_act(dy), as_act(x)
     _check_act(dy, "wgrad dy"); _check_act(x, "wgrad x")
@@ -330,13 +335,16 @@ def conv3x3_wgrad(dy: th.Tensor, x: th.Tensor, *, upsample_in=False, out=None, a
     else:
         dw = out
         assert dw.shape == (cout, cin, 3, 3) and dw.dtype == th.float32 and dw.is_contiguous() and dw.device == dy.device
+    if bias_out is not None:
+        assert bias_out.shape == (cout,) and bias_out.dtype == th.float32 and bias_out.is_contiguous() and bias_out.device == dy.device
     l = _l()
     _account(2.0 * B * H * W * 9 * cin * cout, 2.0 * (x.numel() + dy.numel()))
     ws = _workspace(dy.device, l.mg_conv3x3_wgrad_workspace_bytes(B, H, W, cin, cout), "wgrad")
+    flags = (1 if upsample_in else 0) | (2 if accumulate else 0) | (4 if accumulate_bias else 0)
     with th.cuda.device(dy.device):
-        _lib.check(l.mg_conv3x3_wgrad_bf16(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(),
-                                           B, H, W, cin, cout, (1 if upsample_in else 0) | (2 if accumulate else 0),
-                                           th.cuda.current_stream().cuda_stream), "mg_conv3x3_wgrad_bf16")
+        _lib.check(l.mg_conv3x3_wgrad_bias_bf16(dy.data_ptr(), x.data_ptr(), dw.data_ptr(),
+                                                bias_out.data_ptr() if bias_out is not None else None, ws.data_ptr(), ws.numel(),
+                                                B, H, W, cin, cout, flags, th.cuda.current_stream().cuda_stream), "mg_conv3x3_wgrad_bias_bf16")
     return dw
 
 
@@ -350,13 +358,13 @@ def conv3x3_wgrad(dy: th.Tensor, x: th.Tensor, *, upsample_in=False, out=None, a
 # runs the weight-gradient chain beside the data-gradient chain.
 _lane = [None]
 _lane_streams = {}
+BIAS_IN_WGRAD = os.environ.get("MG_BIAS_IN_WGRAD", "1") != "0"
 
 
 class WgradLane:
     def __init__(self, params, depth: int = None):
         self.params = list(params)
-        self.index = {p.data_ptr(): i for i, p in enumerate(self.params)
-                      if p.requires_grad and p.dim() == 4 and tuple(p.shape[2:]) == (3, 3) and p.shape[0] >= 16 and p.shape[1] >= 16}
+        self.index = {p.data_ptr(): i for i, p in enumerate(self.params) if p.requires_grad}
         self.out = {}
         self.depth = int(os.environ.get("MG_WGRAD_LANE_DEPTH", "6")) if depth is None else depth
         self.pending = collections.deque()
@@ -380,17 +388,27 @@ class WgradLane:
 
     def accepts(self, w: th.Tensor) -> bool:
         # only first-order work (no graph is being recorded through this product) issued from the lane's own stream
-        return (not th.is_grad_enabled()) and w.data_ptr() in self.index and th.cuda.current_stream() == self.origin
+        return ((not th.is_grad_enabled()) and w.dim() == 4 and tuple(w.shape[2:]) == (3, 3) and w.shape[0] >= 16 and w.shape[1] >= 16
+                and w.data_ptr() in self.index and th.cuda.current_stream() == self.origin)
 
-    def submit(self, w: th.Tensor, g: th.Tensor, x: th.Tensor, upsample_in: bool = False) -> None:
-        cur = self.origin
-        i = self.index[w.data_ptr()]
+    def accepts_bias(self, w: th.Tensor, b) -> bool:
+        """The bias gradient of the same convolution can ride on the weight-gradient launch."""
+        return BIAS_IN_WGRAD and b is not None and b.dim() == 1 and b.data_ptr() in self.index and self.accepts(w)
+
+    def _slot(self, p: th.Tensor):
+        i = self.index[p.data_ptr()]
         first = i not in self.out
         if first:
-            self.out[i] = th.empty(tuple(w.shape), dtype=th.float32, device=w.device)
+            self.out[i] = th.empty(tuple(p.shape), dtype=th.float32, device=p.device)
+        return self.out[i], first
+
+    def submit(self, w: th.Tensor, g: th.Tensor, x: th.Tensor, upsample_in: bool = False, bias=None) -> None:
+        cur = self.origin
+        dw, first = self._slot(w)
+        db, first_b = self._slot(bias) if bias is not None else (None, True)
         self.stream.wait_stream(cur)
         with th.cuda.stream(self.stream):
-            conv3x3_wgrad(g, x, upsample_in=upsample_in, out=self.out[i], accumulate=not first)
+            conv3x3_wgrad(g, x, upsample_in=upsample_in, out=dw, accumulate=not first, bias_out=db, accumulate_bias=not first_b)
             ev = th.cuda.Event()
             ev.record(self.stream)
         # g and x were allocated on the origin stream: they stay referenced until that stream has waited for the lane

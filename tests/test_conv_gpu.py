@@ -119,6 +119,28 @@ def test_wgrad(B, Cin, Cout, H, W):
     assert rel_l2(dw, ref) <= 1e-4, rel_l2(dw, ref)       # fp32 accumulate of exact bf16 products
 
 
+@pytest.mark.parametrize("B,Cin,Cout,H,W", SHAPES + [(3, 128, 32, 4, 4), (2, 256, 48, 8, 8), (8, 16, 32, 40, 24)])
+def test_wgrad_with_bias_row(B, Cin, Cout, H, W):
+    """mg_conv3x3_wgrad_bias_bf16: the bias gradient as one more GEMM row (ones), written / accumulated together with dw
+    (also where 9 * Cin is a multiple of 128 and the row opens a block of its own)."""
+    from musicgan_b200.networks import ops
+    x = _mk(B, Cin, H, W, 17)
+    dy = _mk(B, Cout, H, W, 18)
+    ref_w = torch.nn.grad.conv2d_weight(x.float(), (Cout, Cin, 3, 3), dy.float(), padding=1)
+    ref_b = dy.float().sum(dim=(0, 2, 3))
+    dw = torch.full((Cout, Cin, 3, 3), float("nan"), device="cuda")
+    db = torch.full((Cout,), float("nan"), device="cuda")
+    ops.conv3x3_wgrad(dy, x, out=dw, bias_out=db)
+    assert rel_l2(dw, ref_w) <= 1e-4 and rel_l2(db, ref_b) <= 1e-5, (rel_l2(dw, ref_w), rel_l2(db, ref_b))
+    assert torch.equal(dw, ops.conv3x3_wgrad(dy, x))          # the extra row does not disturb the others
+    ops.conv3x3_wgrad(dy, x, out=dw, accumulate=True, bias_out=db, accumulate_bias=True)
+    assert rel_l2(dw, 2 * ref_w) <= 1e-4 and rel_l2(db, 2 * ref_b) <= 1e-5
+    ops.conv3x3_wgrad(dy, x, out=dw, accumulate=True, bias_out=db)      # dw += , db =
+    assert rel_l2(dw, 3 * ref_w) <= 1e-4 and rel_l2(db, ref_b) <= 1e-5
+    ops.conv3x3_wgrad(dy, x, out=dw, accumulate=True)                   # no bias row: db untouched
+    assert rel_l2(dw, 4 * ref_w) <= 1e-4 and rel_l2(db, ref_b) <= 1e-5
+
+
 def test_wgrad_upsampled_input():
     from musicgan_b200.networks import ops
     x = _mk(2, 48, 16, 8, 9)

@@ -288,6 +288,44 @@ def test_graph_replays_equal_eager_steps():
     assert moved > 10
 
 
+@pytest.mark.parametrize("name", ["stage2_b3", "stage4_b2", "stage7_b8"])
+def test_graphed_steps_vs_oracle(name):
+    """The path bench.py and train() run -- graphed.GraphedSteps: two parallel branches, weight gradients on side streams
+    (ops.WgradLane), bias gradients of the bf16 layers from the weight-gradient launch, one-launch weight packing --
+    measured DIRECTLY against the fp32 oracle (train.py:143-214), not only through its equality with the eager steps:
+    critic-step gradient on the scale of its terms and generator-step gradient, rel-L2 <= 1e-2.  The optimisers are SGD
+    with lr 0 so that the warm-up and the replays leave the golden parameters where they are."""
+    from musicgan_b200.graphed import GraphedSteps
+    stage, batch, alpha, z, z2, x_real, eps = case_inputs(name)
+    sd_g, sd_d = no.make_state("gen", stage, 11), no.make_state("disc", stage, 12)
+    gen, disc = build(stage, sd_g, sd_d)
+    og, od = torch.optim.SGD(gen.parameters(), lr=0.0), torch.optim.SGD(disc.parameters(), lr=0.0)
+    gs = GraphedSteps(gen, disc, og, od, batch, 32, 4 * 2 ** stage, alpha, warmup=1, static_noise=True)
+    gs.z.copy_(z.cuda()); gs.eps.copy_(eps.cuda())
+    stats = gs.critic_step(x_real.cuda()).clone()
+    ref = no.d_step(sd_g, sd_d, z, x_real, eps, alpha, stage)
+    assert sorted(k for k, p in disc.named_parameters() if p.grad is None) == sorted(k for k, v in ref["grads"].items() if v is None)
+    g_tot, r_tot = cat_grads(_param_grads(disc), ref["grads"])
+    x_fake = ref["x_fake"]
+    denom = 0.0
+    for oracle in (lambda d: no.disc_forward(d, x_real, alpha, stage).mean(), lambda d: no.disc_forward(d, x_fake, alpha, stage).mean(),
+                   lambda d: no.gradient_penalty(d, x_real, x_fake, alpha, stage, eps)):
+        denom += _norm(_oracle_term_grads(sd_d, oracle))
+    e_terms = (g_tot.double() - r_tot.double()).norm().item() / denom
+    gs.z.copy_(z2.cuda())
+    gstats = gs.generator_step().clone()
+    refg = no.g_step(sd_g, sd_d, z2, alpha, stage)
+    assert sorted(k for k, p in gen.named_parameters() if p.grad is None) == sorted(k for k, v in refg["grads"].items() if v is None)
+    g, r = cat_grads(_param_grads(gen), refg["grads"])
+    e_g = rel(g, r)
+    print(f"{name} (graph replay): critic-step gradient {e_terms:.2e} of the term scale, gp {stats[1].item():.5f} vs {ref['gp'].item():.5f}; "
+          f"G-step gradient rel-L2 {e_g:.2e}, g_loss {gstats[0].item():.5f} vs {refg['loss'].item():.5f}")
+    assert e_terms <= TOL, e_terms
+    assert abs(stats[1].item() - ref["gp"].item()) <= 1e-2 * abs(ref["gp"].item())
+    assert e_g <= TOL, e_g
+    assert abs(gstats[0].item() - refg["loss"].item()) <= 1e-2 * max(abs(refg["loss"].item()), 1e-3)
+
+
 def test_repeated_steps_are_bitwise_reproducible():
     """Race / hazard detector in place of compute-sanitizer (closed on this pool): with programmatic dependent launch,
     early accumulator release, deterministic two-step reductions and the two-stream critic graph, the SAME critic step
