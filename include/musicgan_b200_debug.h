@@ -21,6 +21,11 @@ int mg_debug_umma_gemm(const void* A, const void* B, float* D, int K, int N, int
  * 0x1000 | thread << 4 | (register index + 1); out [128 lanes][32 columns] uint32 = the TMEM block afterwards. */
 int mg_debug_tmem_store(uint32_t* out, int shape, int lane_off, int col_off, mgStream stream);
 
+/* Pacing probe: clock64 ticks one thread needs to issue AND complete a chain of n_mma M128 x N x K16 bf16 MMAs rotating
+ * over n_acc accumulators (1 = each depends on the previous through D).  mode 0: operands in shared memory, 8-row groups
+ * 128 B apart; 1: 160 B apart (the convolutions' halo rows); 2: A operand in TMEM. */
+int mg_debug_mma_pace(long long* cycles_dev, int N, int n_mma, int n_acc, int mode, mgStream stream);
+
 #ifdef __cplusplus
 }
 #endif

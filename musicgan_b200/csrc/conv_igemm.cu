@@ -206,11 +206,14 @@ k_conv3x3(const ConvParams p) {
         //   B: weights are packed [tap][k chunk][n] -> the descriptor simply advances by 2*nt per MMA
         const int nn = p.parts * nt;                   // GEMM N of every MMA: [w | w_lo] side by side when parts == 2
         const uint32_t idesc = instr_desc_bf16(nn, false, false);
-        const uint64_t a_desc0 = smem_desc(smem_u32(sA0), (uint32_t)p.halo_pitch * 16u, kHaloW * 16u);
+        // ablate bit 32 (timing experiment, wrong results): every tap reads 128-byte ALIGNED core matrices of slot 0
+        const bool al = (p.ablate & 32) != 0;
+        const uint64_t a_desc0 = al ? smem_desc((smem_u32(sA0) + 127u) & ~127u, 192u * 16u, 128u)
+                                    : smem_desc(smem_u32(sA0), (uint32_t)p.halo_pitch * 16u, kHaloW * 16u);
         const uint64_t b_desc0 = smem_desc(smem_u32(sW), (uint32_t)nn * 16u, 128u);
         const uint64_t ones_desc = smem_desc(smem_u32(sOnes), 128u * 16u, 128u);
         const uint32_t slot_units = (uint32_t)(nch * p.halo_pitch), b_step = (uint32_t)(2 * nn);
-        const uint32_t a_kstep = 2u * (uint32_t)p.halo_pitch;
+        const uint32_t a_kstep = al ? 2u * 192u : 2u * (uint32_t)p.halo_pitch;
         const int ksteps = nch >> 1;
         mbar_wait(w_full, 0);
         int slot = 0, acc = 0; uint32_t ph = 0, aph = 0;
@@ -219,10 +222,10 @@ k_conv3x3(const ConvParams p) {
             mbar_wait(&full_a[slot], ph);
             if (p.consumer_fence) fence_proxy_async();      // (debug switch) cp.async-written operands -> async proxy
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {       // single-thread region behind ONE elect.sync (see umma.cuh: `lane == 0` costs 4x per MMA)
                 for (int blk = 0; blk < p.mb; ++blk) {
                     const uint32_t d = tmem_base + acc * acc_stride + blk * p.blk_stride;
-                    const uint64_t da_blk = a_desc0 + (uint64_t)(slot * slot_units + blk * (kTileH * kHaloW));
+                    const uint64_t da_blk = a_desc0 + (uint64_t)((al ? 0 : slot * slot_units) + blk * (kTileH * kHaloW));
                     uint64_t db = b_desc0;
                     uint32_t accum = 0;
                     // parts == 2 (w = hi + lo, 16 significand bits, so that LeakyReLU masks agree with the fp32
@@ -233,7 +236,7 @@ k_conv3x3(const ConvParams p) {
                     if (!(p.ablate & 2))
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        uint64_t da = da_blk + (uint64_t)((tap / 3) * kHaloW + (tap % 3));
+                        uint64_t da = da_blk + (uint64_t)(al ? 0 : (tap / 3) * kHaloW + (tap % 3));
                         for (int kk = 0; kk < ksteps; ++kk) {
                             mma_bf16(d, da, db, idesc, accum);
                             accum = 1;
@@ -331,7 +334,7 @@ k_conv3x3(const ConvParams p) {
                         const __nv_bfloat162 h = __floats2bfloat162_rn(t0, t1);
                         pk[j] = *reinterpret_cast<const uint32_t*>(&h);
                     }
-                    if (valid && !((p.ablate & 8) && pk[0] == 0x12345678u)) {
+                    if (valid && (!(p.ablate & 8) || pk[0] == 0x12345678u)) {
                         // one 256-bit store = one full 32-byte sector per thread (two 16-byte stores reach L2 as two
                         // partial-sector writes)
                         asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"

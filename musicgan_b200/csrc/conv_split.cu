@@ -183,7 +183,7 @@ k_conv3x3_split(const SplitParams p) {
         for (int cg = 0; cg < n_cg; ++cg) {
             mbar_wait(&full[slot], ph);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {       // single-thread region behind ONE elect.sync (umma.cuh)
                 const uint32_t sA = smem_u32(smem + (size_t)slot * p.stage_bytes);
                 const uint64_t a_hi = smem_desc(sA, (uint32_t)kHaloPitch * 16u, kHaloW * 16u);
                 const uint64_t a_lo = smem_desc(sA + kSplitAPlane, (uint32_t)kHaloPitch * 16u, kHaloW * 16u);

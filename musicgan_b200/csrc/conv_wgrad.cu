@@ -191,7 +191,7 @@ k_conv3x3_wgrad(const WgradParams p) {
             mbar_wait(&full[slot], ph);
             mbar_wait(&a_full[buf], aph);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {       // single-thread region behind ONE elect.sync (umma.cuh)
                 const uint64_t db0 = b_desc0 + (uint64_t)(slot * stage_units);
                 for (int j = mw; j < ((p.ablate & 2) ? 0 : nb); j += kWgradMmaWarps) {
                     const uint32_t d = tmem_base + j * p.Cout;
@@ -212,7 +212,7 @@ k_conv3x3_wgrad(const WgradParams p) {
             if (++slot == p.stages) { slot = 0; ph ^= 1u; }
             if (++buf == 2) { buf = 0; aph ^= 1u; }
         }
-        if (lane == 0) mma_commit(done);
+        if (elect_one()) mma_commit(done);      // the lane that issued the MMAs
         __syncwarp();
     } else {
         // ================= transposers: shifted x windows, smem -> TMEM A operand; then the final flush =================

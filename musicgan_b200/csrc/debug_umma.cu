@@ -166,3 +166,105 @@ extern "C" int mg_debug_tmem_store(uint32_t* out, int shape, int lane_off, int c
     k_debug_tmem_store<<<1, 128, 0, (cudaStream_t)stream>>>(out, shape, lane_off, col_off);
     return check_launch("k_debug_tmem_store");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Pacing probe: how many cycles does ONE elected thread need per M128 x N x K16 bf16 tcgen05.mma when it issues a chain
+// of `n_mma` of them (operand contents irrelevant)?  n_acc: the chain rotates over that many accumulators (1 = every
+// MMA depends on the previous one through D).  mode 0: A, B from shared memory, canonical no-swizzle, 8-row groups 128 B
+// apart (aligned);  1: the same with the groups 160 B apart (the convolution's halo rows);  2: A from TMEM.
+// cycles[0] = clock64 ticks from the first issue to the completion of the last MMA.
+// ------------------------------------------------------------------------------------------------
+namespace mg {
+__global__ void __launch_bounds__(128)
+k_debug_mma_pace(long long* __restrict__ cycles, int N, int n_mma, int n_acc, int mode) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 48 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == 0) tmem_alloc(&tmem_base, 512);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = tmem_base;
+    if (tid == 0 && mode < 4) {
+        const uint32_t idesc = instr_desc_bf16(N, false, false);
+        const uint32_t a0 = (smem_u32(smem) + 127u) & ~127u, b0 = a0 + 24 * 1024;
+        const uint64_t da = smem_desc(a0, 3072u, mode == 1 ? 160u : 128u);
+        const uint64_t db = smem_desc(b0, (uint32_t)N * 16u, 128u);
+        const uint32_t tm_a = tm + 448;
+        const long long t0 = clock64();
+        for (int i = 0; i < n_mma; ++i) {
+            const uint32_t d = tm + (uint32_t)((i % n_acc) * N);
+            if (mode == 2) mma_bf16_ts(d, tm_a, db, idesc, 1u);
+            else mma_bf16(d, da, db, idesc, 1u);
+        }
+        mma_commit(&bar);
+        mbar_wait(&bar, 0);
+        cycles[0] = clock64() - t0;
+    }
+    // modes 8 / 9: ONE elect.sync, then the whole chain as single-thread code (9: unrolled by 8, descriptors stepping like
+    // the convolution's taps)
+    if (warp == 1 && mode >= 8) {
+        const uint32_t idesc = instr_desc_bf16(N, false, false);
+        const uint32_t a0 = (smem_u32(smem) + 127u) & ~127u, b0 = a0 + 24 * 1024;
+        const uint64_t da0 = smem_desc(a0, 3072u, 160u);
+        const uint64_t db0 = smem_desc(b0, (uint32_t)N * 16u, 128u);
+        const long long t0 = clock64();
+        if (elect_one()) {
+            if (mode == 8) {
+                int acc = 0;
+                for (int i = 0; i < n_mma; ++i) {
+                    mma_bf16(tm + (uint32_t)(acc * N), da0, db0, idesc, 1u);
+                    if (++acc == n_acc) acc = 0;
+                }
+            } else {
+                for (int i = 0; i < n_mma; i += 8) {
+                    uint64_t da = da0, db = db0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        mma_bf16(tm, da, db, idesc, 1u);
+                        da += 1; db += 2;
+                    }
+                }
+            }
+            mma_commit(&bar);
+        }
+        __syncwarp();
+        mbar_wait(&bar, 0);
+        if ((tid & 31) == 0) cycles[0] = clock64() - t0;
+    }
+    // modes 4 / 5 / 6: the same chains (as modes 0 / 1 / 2) issued warp-convergently (all lanes of warp 1, elect.sync)
+    if (warp == 1 && mode >= 4 && mode < 8) {
+        const uint32_t idesc = instr_desc_bf16(N, false, false);
+        const uint32_t a0 = (smem_u32(smem) + 127u) & ~127u, b0 = a0 + 24 * 1024;
+        const uint64_t da = smem_desc(a0, 3072u, mode == 5 ? 160u : 128u);
+        const uint64_t db = smem_desc(b0, (uint32_t)N * 16u, 128u);
+        const uint32_t tm_a = tm + 448;
+        const long long t0 = clock64();
+        int acc = 0;
+        for (int i = 0; i < n_mma; ++i) {
+            const uint32_t d = tm + (uint32_t)(acc * N);
+            if (mode == 6) mma_bf16_ts_warp(d, tm_a, db, idesc, 1u);
+            else mma_bf16_warp(d, da, db, idesc, 1u);
+            if (++acc == n_acc) acc = 0;
+        }
+        mma_commit_warp(&bar);
+        mbar_wait(&bar, 0);
+        if ((tid & 31) == 0) cycles[0] = clock64() - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 512);
+}
+}  // namespace mg
+
+extern "C" int mg_debug_mma_pace(long long* cycles, int N, int n_mma, int n_acc, int mode, mgStream stream) {
+    using namespace mg;
+    if (!cycles || N % 16 || N < 16 || N > 256 || n_acc < 1 || n_acc * N > 448 || n_mma < 1) return MG_ERR_BAD_ARG;
+    cudaFuncSetAttribute(k_debug_mma_pace, cudaFuncAttributeMaxDynamicSharedMemorySize, 49 * 1024);
+    k_debug_mma_pace<<<1, 128, 49 * 1024, (cudaStream_t)stream>>>(cycles, N, n_mma, n_acc, mode);
+    return check_launch("k_debug_mma_pace");
+}

@@ -140,5 +140,47 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+
+// ---- warp-convergent issue -------------------------------------------------------------------------------------------
+// tcgen05.mma / tcgen05.commit take their operands from UNIFORM registers.  Issued inside `if (lane == 0)` the operands
+// are per-thread registers of a diverged warp and ptxas wraps every instruction in a serialising ELECT / R2UR /
+// BRA.U.ANY loop: ~200 cycles per MMA per issuing thread (measured, scripts/probe_mma_pace.py), whatever the shape.  The
+// variants below are executed by ALL 32 lanes of the issuing warp with warp-uniform arguments; elect.sync picks the
+// issuing lane (the same one every time for a full mask), and the instruction goes out at the tensor pipe's own pace.
+__device__ __forceinline__ void mma_bf16_warp(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p, e;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ts_warp(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p, e;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// true in exactly one lane of a converged warp (the same lane every time); everything inside `if (elect_one()) { ... }`
+// is single-thread code whose R2UR moves need no serialising loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n.reg .pred e;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "@e mov.u32 %0, 1;\n}"
+        : "+r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mma_commit_warp(uint64_t* bar) {
+    asm volatile(
+        "{\n.reg .pred e;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}"
+        ::"r"(smem_u32(bar)) : "memory");
+}
+
 }  // namespace umma
 }  // namespace mg
