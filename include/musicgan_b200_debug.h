@@ -25,6 +25,9 @@ int mg_debug_tmem_store(uint32_t* out, int shape, int lane_off, int col_off, mgS
  * over n_acc accumulators (1 = each depends on the previous through D).  mode 0: operands in shared memory, 8-row groups
  * 128 B apart; 1: 160 B apart (the convolutions' halo rows); 2: A operand in TMEM. */
 int mg_debug_mma_pace(long long* cycles_dev, int N, int n_mma, int n_acc, int mode, mgStream stream);
+/* The single-thread-region chain on `ctas` CTAs at once (128 TMEM columns, 49 KB of shared memory each: up to four share
+ * an SM); cycles_dev[cta] = that CTA's ticks. */
+int mg_debug_mma_pace_grid(long long* cycles_dev, int N, int n_mma, int ctas, mgStream stream);
 
 #ifdef __cplusplus
 }

@@ -453,9 +453,9 @@ static ConvPlan plan_conv(int Cin, int Cout, bool need_full_n, int H = 0, int pa
     //    (barrier round trips, tile index arithmetic, commit) by mb and shrinks the halo overhead.  Requirements: the
     //    per-thread chunk table of the producers stays in registers, >= 3 halo slots, >= 2 accumulators, and the
     //    TMEM columns of all resident CTAs fit in 512.
-    static const int force_occ = getenv("MG_CONV_OCC") ? atoi(getenv("MG_CONV_OCC")) : 0;
-    static const int force_mb = getenv("MG_CONV_MB") ? atoi(getenv("MG_CONV_MB")) : 0;
-    static const int force_acc = getenv("MG_CONV_ACC") ? atoi(getenv("MG_CONV_ACC")) : 0;
+    const int force_occ = getenv("MG_CONV_OCC") ? atoi(getenv("MG_CONV_OCC")) : 0;
+    const int force_mb = getenv("MG_CONV_MB") ? atoi(getenv("MG_CONV_MB")) : 0;
+    const int force_acc = getenv("MG_CONV_ACC") ? atoi(getenv("MG_CONV_ACC")) : 0;
     static const int prefs[8][2] = {{2, 4}, {1, 4}, {2, 3}, {1, 3}, {4, 2}, {2, 2}, {1, 2}, {1, 1}};
     for (int pass = 0; pass < 2; ++pass) {            // pass 1 ignores the debug overrides if they leave no candidate
         for (const auto& c : prefs) {

@@ -309,7 +309,7 @@ static SplitPlan plan_split(int Cin, int Cout, bool full_n, int n_tiles, int wpa
     SplitPlan pl{};
     // layers with several waves of tiles run TWO CTAs per SM (each gets half of the shared memory, i.e. a shorter ring):
     // load, MMA and epilogue phases of neighbouring tiles then overlap; small layers keep one CTA with a deep ring
-    static const int two_cta_tiles = getenv("MG_SPLIT_2CTA_TILES") ? atoi(getenv("MG_SPLIT_2CTA_TILES")) : 0;
+    const int two_cta_tiles = getenv("MG_SPLIT_2CTA_TILES") ? atoi(getenv("MG_SPLIT_2CTA_TILES")) : 0;
     const size_t budget = (!full_n && two_cta_tiles > 0 && n_tiles >= two_cta_tiles ? 108 : 216) * 1024;
     // slice width.  An M128 x N x K16 MMA from shared memory costs max(32, N / 2) cycles (the A tile is re-read by every
     // MMA), so N <= 64 is as fast per CTA as it gets: layers with fewer tiles than SMs (latency bound) use narrow slices

@@ -26,10 +26,11 @@ namespace mg {
 using namespace umma;
 
 constexpr int kDyPitch = 129;          // pixels per channel chunk of the staged dy tile (B operand)
-constexpr int kWgradMmaWarps = 3;      // row blocks are dealt round-robin to three MMA-issuing warps
+constexpr int kWgradMmaWarps = 3;      // row blocks are dealt round-robin to three MMA-issuing warps (one warp: D0.conv1 76 -> 85 us)
 constexpr int kXposeWarps = 8;         // x halo: smem -> registers -> TMEM (A operand), two warps per TMEM lane quarter
 constexpr int kWgradThreads = (kXposeWarps + 4 + kWgradMmaWarps) * 32;     // 480
-constexpr int kMaxBlocks = 4;          // row blocks per CTA (TMEM: nb * (Cout + 2 * 64) columns)
+constexpr int kMaxBlocks = 4;          // row blocks per CTA (TMEM: nb * (Cout + a_bufs * 64) columns)
+constexpr int kMaxABufs = 4;           // A-operand buffers in TMEM (transposers run that many tiles ahead of the MMAs)
 
 struct WgradParams {
     const __nv_bfloat16* dy;    // [B][H][W][Cout]
@@ -44,6 +45,7 @@ struct WgradParams {
     int tiles_per_img;
     FastDiv div_img, div_tx;
     int ablate;                 // debug (MG_WGRAD_ABLATE): 1 no copies, 2 no MMAs, 4 no operand staging (ldmatrix / tcgen05.st)
+    int a_bufs;                 // A-operand buffers in TMEM (2 .. kMaxABufs, as many as the 512 columns allow)
     int bias_row;               // 9 * Cin: an A row of ones whose products are the bias gradient sum_pixels dy[.][co]; -1 = none
 };
 
@@ -63,15 +65,15 @@ k_conv3x3_wgrad(const WgradParams p) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_offset);
     uint64_t* full = bars;                    // [kMaxStages]  producers -> transposers + MMA
     uint64_t* empty = bars + kMaxStages;      // [kMaxStages]  MMA commit -> producers
-    uint64_t* a_full = bars + 2 * kMaxStages; // [2]           transposers -> MMA
-    uint64_t* a_empty = a_full + 2;           // [2]           MMA commit -> transposers
-    uint64_t* done = a_full + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 5);
+    uint64_t* a_full = bars + 2 * kMaxStages; // [kMaxABufs]   transposers -> MMA
+    uint64_t* a_empty = a_full + kMaxABufs;   // [kMaxABufs]   MMA commit -> transposers
+    uint64_t* done = a_full + 2 * kMaxABufs;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 2 * kMaxABufs + 1);
 
     constexpr int kProd0 = kXposeWarps, kMma0 = kXposeWarps + 4;
     if (tid0 == 0) {
-        for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], kWgradMmaWarps + kXposeWarps); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], kXposeWarps); mbar_init(&a_empty[i], kWgradMmaWarps); }
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], (p.ablate & 8) ? 4 : 128); mbar_init(&empty[i], kWgradMmaWarps + kXposeWarps); }
+        for (int i = 0; i < kMaxABufs; ++i) { mbar_init(&a_full[i], kXposeWarps); mbar_init(&a_empty[i], kWgradMmaWarps); }
         mbar_init(done, kWgradMmaWarps);
         mbar_fence_init();
     }
@@ -84,7 +86,7 @@ k_conv3x3_wgrad(const WgradParams p) {
     // re-reads %tid.x (S2R, tens of cycles) inside every per-tile loop instead of keeping it in a register.
     const int tid = tid0 | (int)(tmem_base & 1u), warp = tid >> 5, lane = tid & 31;
     const int a_cols = p.blocks_per_cta * 64;                                  // columns of one A buffer
-    const uint32_t tmem_a = tmem_base + (uint32_t)(p.tmem_cols - 2 * a_cols);  // two A buffers at the top
+    const uint32_t tmem_a = tmem_base + (uint32_t)(p.tmem_cols - p.a_bufs * a_cols);  // the A buffers at the top
     pdl_trigger();               // only after the TMEM allocation (see k_conv3x3: a dependent must not allocate first)
     pdl_wait();                  // everything above overlapped the previous kernel's tail; global memory from here on
 
@@ -177,7 +179,8 @@ k_conv3x3_wgrad(const WgradParams p) {
                 const void* src = ok ? (const void*)(reinterpret_cast<const uint4*>(xb + ((size_t)sy * p.Win + sx) * p.Cin) + c) : (const void*)p.x;
                 cp_async16(s_x + (uint32_t)(c * kHaloPitch + pos) * 16u, src, ok ? 16u : 0u);
             }
-            cp_async_arrive(&full[slot]);
+            if (p.ablate & 8) { if (lane == 0) mbar_arrive(&full[slot]); }      // timing experiment: 4 arrivals instead of 128
+            else cp_async_arrive(&full[slot]);
             if (++slot == p.stages) { slot = 0; ph ^= 1u; }
         }
     } else if (warp >= kMma0) {
@@ -210,7 +213,7 @@ k_conv3x3_wgrad(const WgradParams p) {
             accum = 1;
             __syncwarp();
             if (++slot == p.stages) { slot = 0; ph ^= 1u; }
-            if (++buf == 2) { buf = 0; aph ^= 1u; }
+            if (++buf == p.a_bufs) { buf = 0; aph ^= 1u; }
         }
         if (elect_one()) mma_commit(done);      // the lane that issued the MMAs
         __syncwarp();
@@ -252,7 +255,7 @@ k_conv3x3_wgrad(const WgradParams p) {
                 uint32_t r[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) r[k] = L == (p.bias_row & 127) ? 0x3F803F80u : 0u;
-                for (int b2 = 0; b2 < 2; ++b2)
+                for (int b2 = 0; b2 < p.a_bufs; ++b2)
                     for (int c = 0; c < 4; ++c)
                         tmem_st8(tmem_a + b2 * a_cols + jb * 64 + khalf * 32 + c * 8 + lane_addr, r);
                 tmem_wait_st();
@@ -288,7 +291,7 @@ k_conv3x3_wgrad(const WgradParams p) {
                 mbar_arrive(&empty[slot]);   // this warp no longer reads the smem slot (the MMA warps commit theirs)
             }
             if (++slot == p.stages) { slot = 0; ph ^= 1u; }
-            if (++buf == 2) { buf = 0; aph ^= 1u; }
+            if (++buf == p.a_bufs) { buf = 0; aph ^= 1u; }
         }
         {   // final flush: every CTA writes its accumulators ONCE, with plain 16-byte stores, to its own slice of the
             // workspace (k_wgrad_reduce sums the slices: no atomics, deterministic order, no pre-zeroed output)
@@ -411,13 +414,20 @@ extern "C" int mg_conv3x3_wgrad_bias_bf16(const void* dy, const void* x, float* 
     p.blocks_per_cta = nb;
     int cols = 32; while (cols < nb * (Cout + 128)) cols <<= 1;
     p.tmem_cols = cols;
+    {   // spare columns become further A buffers: the operand staging then runs more tiles ahead of the MMAs
+        const int forced = getenv("MG_WGRAD_ABUFS") ? atoi(getenv("MG_WGRAD_ABUFS")) : 0;
+        int a_bufs = (cols - nb * Cout) / (nb * 64);
+        a_bufs = a_bufs > kMaxABufs ? kMaxABufs : a_bufs;
+        if (forced >= 2 && forced <= a_bufs) a_bufs = forced;
+        p.a_bufs = a_bufs;
+    }
     const int occ = 1;
     const size_t stage_bytes = (size_t)(Cout / 8) * kDyPitch * 16 + (size_t)(Cin / 8) * kHaloPitch * 16;
     int stages = kMaxStages;
     size_t smem = 0;
     for (; stages >= 1; --stages) {
         const size_t need = (size_t)stages * stage_bytes;
-        smem = align_up(need, 16) + 256;
+        smem = align_up(need, 16) + 320;       // barriers: 2 * kMaxStages + 2 * kMaxABufs + 1, TMEM slot
         if (smem <= 200 * 1024) { p.bar_offset = (unsigned)align_up(need, 16); break; }
     }
     if (stages < 1) return MG_ERR_UNSUPPORTED;

@@ -176,13 +176,14 @@ extern "C" int mg_debug_tmem_store(uint32_t* out, int shape, int lane_off, int c
 // ------------------------------------------------------------------------------------------------
 namespace mg {
 __global__ void __launch_bounds__(128)
-k_debug_mma_pace(long long* __restrict__ cycles, int N, int n_mma, int n_acc, int mode) {
+k_debug_mma_pace(long long* __restrict__ cycles, int N, int n_mma, int n_acc, int mode, int tmem_cols) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, bar2;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) mbar_init(&bar2, 100000);
     for (int i = tid; i < 48 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    if (warp == 0) tmem_alloc(&tmem_base, 512);
+    if (warp == 0) tmem_alloc(&tmem_base, tmem_cols);
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     fence_proxy_async();
     tc_fence_before();
@@ -214,7 +215,19 @@ k_debug_mma_pace(long long* __restrict__ cycles, int N, int n_mma, int n_acc, in
         const uint64_t db0 = smem_desc(b0, (uint32_t)N * 16u, 128u);
         const long long t0 = clock64();
         if (elect_one()) {
-            if (mode == 8) {
+            if (mode == 11) {      // as mode 8, for many co-resident CTAs (grid > 1): two accumulators
+                int acc = 0;
+                for (int i = 0; i < n_mma; ++i) {
+                    mma_bf16(tm + (uint32_t)(acc * N), da0, db0, idesc, 1u);
+                    acc ^= 1;
+                }
+            } else if (mode == 10) {      // a tcgen05.commit (to a barrier nobody waits on) after every n_acc MMAs, rotating 2 accumulators
+                int run = 0, acc = 0;
+                for (int i = 0; i < n_mma; ++i) {
+                    mma_bf16(tm + (uint32_t)(acc * N), da0, db0, idesc, 1u);
+                    if (++run == n_acc) { run = 0; acc ^= 1; mma_commit(&bar2); }
+                }
+            } else if (mode == 8) {
                 int acc = 0;
                 for (int i = 0; i < n_mma; ++i) {
                     mma_bf16(tm + (uint32_t)(acc * N), da0, db0, idesc, 1u);
@@ -234,7 +247,7 @@ k_debug_mma_pace(long long* __restrict__ cycles, int N, int n_mma, int n_acc, in
         }
         __syncwarp();
         mbar_wait(&bar, 0);
-        if ((tid & 31) == 0) cycles[0] = clock64() - t0;
+        if ((tid & 31) == 0) cycles[blockIdx.x] = clock64() - t0;
     }
     // modes 4 / 5 / 6: the same chains (as modes 0 / 1 / 2) issued warp-convergently (all lanes of warp 1, elect.sync)
     if (warp == 1 && mode >= 4 && mode < 8) {
@@ -257,14 +270,22 @@ k_debug_mma_pace(long long* __restrict__ cycles, int N, int n_mma, int n_acc, in
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tm, 512);
+    if (warp == 0) tmem_dealloc(tm, tmem_cols);
 }
 }  // namespace mg
 
+extern "C" int mg_debug_mma_pace_grid(long long* cycles, int N, int n_mma, int ctas, mgStream stream) {
+    using namespace mg;
+    if (!cycles || N % 16 || N < 16 || N > 64 || ctas < 1 || n_mma < 1) return MG_ERR_BAD_ARG;
+    cudaFuncSetAttribute(k_debug_mma_pace, cudaFuncAttributeMaxDynamicSharedMemorySize, 49 * 1024);
+    k_debug_mma_pace<<<ctas, 128, 49 * 1024, (cudaStream_t)stream>>>(cycles, N, n_mma, 2, 11, 128);
+    return check_launch("k_debug_mma_pace");
+}
+
 extern "C" int mg_debug_mma_pace(long long* cycles, int N, int n_mma, int n_acc, int mode, mgStream stream) {
     using namespace mg;
-    if (!cycles || N % 16 || N < 16 || N > 256 || n_acc < 1 || n_acc * N > 448 || n_mma < 1) return MG_ERR_BAD_ARG;
+    if (!cycles || N % 16 || N < 16 || N > 256 || n_acc < 1 || (mode != 10 && n_acc * N > 448) || n_mma < 1) return MG_ERR_BAD_ARG;
     cudaFuncSetAttribute(k_debug_mma_pace, cudaFuncAttributeMaxDynamicSharedMemorySize, 49 * 1024);
-    k_debug_mma_pace<<<1, 128, 49 * 1024, (cudaStream_t)stream>>>(cycles, N, n_mma, n_acc, mode);
+    k_debug_mma_pace<<<1, 128, 49 * 1024, (cudaStream_t)stream>>>(cycles, N, n_mma, n_acc, mode, 512);
     return check_launch("k_debug_mma_pace");
 }

@@ -8,7 +8,7 @@ l.mg_debug_mma_pace.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.
 out = th.zeros(1, dtype=th.int64, device="cuda")
 n_mma = 256
 print("cycles per MMA (chain of %d)  mode 0 smem aligned / 1 smem 160-byte groups / 2 A in TMEM; +4: issued warp-convergently (elect.sync)" % n_mma)
-for mode in (0, 4, 8, 9):
+for mode in (8,):
     for N in (32, 64, 128, 256):
         row = []
         for n_acc in (1, 2, 4):
@@ -20,3 +20,26 @@ for mode in (0, 4, 8, 9):
                 th.cuda.synchronize()
             row.append(f"{out.item() / n_mma:6.1f}")
         print(f"mode {mode} N {N:3d}:  n_acc 1/2/4 = {' '.join(row)}")
+
+print("mode 10: a commit after every P MMAs (two accumulators in rotation); cycles per MMA")
+for N in (32, 64, 128):
+    row = []
+    for period in (1, 2, 5, 10, 20, 40):
+        for _ in range(2):
+            assert l.mg_debug_mma_pace(out.data_ptr(), N, 240, period, 10, None) == 0
+            th.cuda.synchronize()
+        row.append(f"P={period}: {out.item() / 240:6.1f}")
+    print(f"N {N:3d}: " + "  ".join(row))
+
+print("co-resident CTAs sharing one tensor pipe: per-CTA cycles per MMA (median), SM-level cycles per MMA")
+l.mg_debug_mma_pace_grid.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p]
+sms = th.cuda.get_device_properties(0).multi_processor_count
+for N in (32, 64):
+    for per_sm in (1, 2, 3, 4):
+        ctas = sms * per_sm
+        buf = th.zeros(ctas, dtype=th.int64, device="cuda")
+        for _ in range(2):
+            assert l.mg_debug_mma_pace_grid(buf.data_ptr(), N, 512, ctas, None) == 0
+            th.cuda.synchronize()
+        med = buf.double().median().item() / 512
+        print(f"N {N:3d}  {per_sm} CTA/SM: per-CTA {med:6.1f}  -> per SM {med / per_sm:6.1f}   (max {buf.max().item() / 512:6.1f})")
