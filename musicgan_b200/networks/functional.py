@@ -76,16 +76,29 @@ def _wgrad(w, g, x, upsample_in: bool = False, bias=None):
     return ConvWgrad.apply(g, x)
 
 
+# The gradient penalty's double backward reaches the FORWARD graph of the critic only through the saved activations of
+# the mask kernels (LReLUBwd / UnpoolLReLUBwd / the 1x1 maps), whose gradient is None -- LeakyReLU masks are piecewise
+# constant.  The autograd engine still runs every forward node it can reach, and a Function that lets torch materialise
+# its missing output gradient is then called with ZEROS: the whole critic backward (18 data gradients, 18 weight gradients
+# + their reduce kernels and casts, the mask / un-pool / 1x1 kernels) ran once per critic step on zeros.  Every Function
+# here therefore switches materialisation off and answers a None gradient with Nones, without a launch.
+def _nones(ctx):
+    return (None,) * len(ctx.needs_input_grad)
+
+
 class ConvFprop(Function):
     """y = conv3x3(x, w), no bias / activation (linear in x and in w)."""
 
     @staticmethod
     def forward(ctx, x, w):
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(x, w)
         return ops.conv3x3(_act(x), w.float().contiguous())
 
     @staticmethod
     def backward(ctx, gy):
+        if gy is None:
+            return _nones(ctx)
         x, w = ctx.saved_tensors
         gx = ConvDgrad.apply(gy, w) if ctx.needs_input_grad[0] else None
         gw = _wgrad(w, gy, x) if ctx.needs_input_grad[1] and _param_grads[0] else None
@@ -97,11 +110,14 @@ class ConvDgrad(Function):
 
     @staticmethod
     def forward(ctx, g, w):
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(g, w)
         return ops.conv3x3(_act(g), w.float().contiguous(), dgrad=True)
 
     @staticmethod
     def backward(ctx, gdx):
+        if gdx is None:
+            return _nones(ctx)
         g, w = ctx.saved_tensors
         gg = ConvFprop.apply(gdx, w) if ctx.needs_input_grad[0] else None
         gw = _wgrad(w, g, gdx) if ctx.needs_input_grad[1] and _param_grads[0] else None
@@ -113,11 +129,14 @@ class ConvWgrad(Function):
 
     @staticmethod
     def forward(ctx, g, x):
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(g, x)
         return ops.conv3x3_wgrad(_act(g), _act(x))
 
     @staticmethod
     def backward(ctx, gdw):
+        if gdw is None:
+            return _nones(ctx)
         g, x = ctx.saved_tensors
         gg = ConvFprop.apply(x, gdw) if ctx.needs_input_grad[0] else None
         gx = ConvDgrad.apply(g, gdw) if ctx.needs_input_grad[1] else None
@@ -137,12 +156,15 @@ class ConvBiasLReLU(Function):
 
     @staticmethod
     def forward(ctx, x, w, b):
+        ctx.set_materialize_grads(False)
         y = ops.conv3x3(_act(x), w.float().contiguous(), b.float().contiguous(), lrelu=True, split_w=True, exact_w=True)
         ctx.save_for_backward(x, w, y, b)
         return y
 
     @staticmethod
     def backward(ctx, gy):
+        if gy is None:
+            return _nones(ctx)
         x, w, y, b = ctx.saved_tensors
         want_gw = ctx.needs_input_grad[1] and _param_grads[0]
         want_gb = ctx.needs_input_grad[2] and _param_grads[0]
@@ -212,12 +234,15 @@ class ConvBiasLReLUPool(Function):
 
     @staticmethod
     def forward(ctx, x, w, b):
+        ctx.set_materialize_grads(False)
         h = ops.conv3x3(_act(x), w.float().contiguous(), b.float().contiguous(), lrelu=True, split_w=True, exact_w=True)
         ctx.save_for_backward(x, w, h, b)
         return ops.pool2(h)
 
     @staticmethod
     def backward(ctx, gp):
+        if gp is None:
+            return _nones(ctx)
         x, w, h, b = ctx.saved_tensors
         want_gw = ctx.needs_input_grad[1] and _param_grads[0]
         want_gb = ctx.needs_input_grad[2] and _param_grads[0]
@@ -276,6 +301,7 @@ class RgbExpand(Function):
 
     @staticmethod
     def forward(ctx, x, w, b, mask_src, lrelu: bool, out_dtype=th.bfloat16):
+        ctx.set_materialize_grads(False)
         y = ops.rgb_expand(x, w, b, mask_src=mask_src, lrelu=lrelu, out_dtype=out_dtype)
         ctx.save_for_backward(x, w, y if lrelu else mask_src)
         ctx.has_mask = lrelu or mask_src is not None
@@ -284,6 +310,8 @@ class RgbExpand(Function):
 
     @staticmethod
     def backward(ctx, gy):
+        if gy is None:
+            return _nones(ctx)
         x, w, m = ctx.saved_tensors
         m = m if ctx.has_mask else None
         gx = RgbProject.apply(gy, w, m) if ctx.needs_input_grad[0] else None
@@ -299,12 +327,15 @@ class RgbProject(Function):
 
     @staticmethod
     def forward(ctx, a, w, mask_src):
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(a, w, mask_src)
         ctx.w_shape = w.shape
         return ops.rgb_project(_act(a), w, mask_src=mask_src, w_is_c_by_2=True)
 
     @staticmethod
     def backward(ctx, gout):
+        if gout is None:
+            return _nones(ctx)
         a, w, m = ctx.saved_tensors
         ga = RgbExpand.apply(gout, w, None, m, False, a.dtype) if ctx.needs_input_grad[0] else None
         gw = None
@@ -362,20 +393,26 @@ class Pool2(Function):
 
     @staticmethod
     def forward(ctx, x):
+        ctx.set_materialize_grads(False)
         return ops.pool2(_act(x))
 
     @staticmethod
     def backward(ctx, g):
+        if g is None:
+            return _nones(ctx)
         return Unpool2.apply(g)
 
 
 class Unpool2(Function):
     @staticmethod
     def forward(ctx, g):
+        ctx.set_materialize_grads(False)
         return ops.pool2(_act(g), adjoint=True)
 
     @staticmethod
     def backward(ctx, gg):
+        if gg is None:
+            return _nones(ctx)
         return Pool2.apply(gg)
 
 
@@ -384,18 +421,24 @@ class PoolPlanes(Function):
 
     @staticmethod
     def forward(ctx, x):
+        ctx.set_materialize_grads(False)
         return ops.pool2_planes(x)
 
     @staticmethod
     def backward(ctx, g):
+        if g is None:
+            return _nones(ctx)
         return UnpoolPlanes.apply(g)
 
 
 class UnpoolPlanes(Function):
     @staticmethod
     def forward(ctx, g):
+        ctx.set_materialize_grads(False)
         return ops.pool2_planes(g, adjoint=True)
 
     @staticmethod
     def backward(ctx, gg):
+        if gg is None:
+            return _nones(ctx)
         return PoolPlanes.apply(gg)
