@@ -25,10 +25,11 @@ def _wav_sample_count(path: str) -> int:
 
 def create_dataset(audio_path: str, dataset_output_dir: str, *, packed: bool = False) -> None:
     w_p = glob.glob(audio_path)
-    if not exists(dataset_output_dir):
+    try:                      # every rank of a torchrun launch gets here: creating must not race with testing
         mkdir(dataset_output_dir)
-    elif exists(dataset_output_dir) and not isdir(dataset_output_dir):
-        raise NotADirectoryError(f"\"{dataset_output_dir}\" is not a directory")
+    except FileExistsError:
+        if not isdir(dataset_output_dir):
+            raise NotADirectoryError(f"\"{dataset_output_dir}\" is not a directory") from None
 
     nb_vec = audio.N_VEC
     rank, ws = parallel.world()

@@ -13,10 +13,11 @@ from .networks import Generator
 
 def generate(output_dir: str, rand_channels: int, gen_dict_state: str, nb_vec: int, nb_music: int,
              sub_batch: int = 4) -> None:
-    if not exists(output_dir):
+    try:                      # every rank of a torchrun launch gets here: creating must not race with testing
         mkdir(output_dir)
-    elif exists(output_dir) and not isdir(output_dir):
-        raise NotADirectoryError(f"\"{output_dir}\" is not a directory")
+    except FileExistsError:
+        if not isdir(output_dir):
+            raise NotADirectoryError(f"\"{output_dir}\" is not a directory") from None
 
     print("Load model...")
     gen = Generator(rand_channels, end_layer=7)

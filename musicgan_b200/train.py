@@ -36,10 +36,11 @@ def train(run_name: str, input_dataset_path: str, output_dir: str, *,
           fadein_lengths=(1, 25000, 37500, 50000, 62500, 75000, 87500, 100000)) -> None:
     assert isdir(input_dataset_path), \
         f"\"{input_dataset_path}\" doesn't exist or is not a directory"
-    if not exists(output_dir):
+    try:                      # every rank of a torchrun launch gets here: creating must not race with testing
         mkdir(output_dir)
-    elif exists(output_dir) and not isdir(output_dir):
-        raise NotADirectoryError(f"\"{output_dir}\" is not a directory !")
+    except FileExistsError:
+        if not isdir(output_dir):
+            raise NotADirectoryError(f"\"{output_dir}\" is not a directory !") from None
 
     rank, ws = parallel.world()
     if seed is not None:
