@@ -62,18 +62,26 @@ def _lane_bias(w, b, act: th.Tensor) -> bool:
     return lane is not None and act.dtype == th.bfloat16 and lane.accepts_bias(w, b)
 
 
-def _wgrad(w, g, x, upsample_in: bool = False, bias=None):
+def _wgrad(w, g, x, upsample_in: bool = False, bias=None, scale=None):
     """Weight gradient of a block: handed to the step's weight-gradient lane when one is open and takes this parameter
     (ops.WgradLane: computed on a second stream, collected by the step; autograd sees None), else computed in line.
-    `bias`: only after _lane_bias(w, bias) said yes."""
+    `bias`: only after _lane_bias(w, bias) said yes.  `scale`: the layer ran with the weight w * scale (0-dim tensor)."""
     lane = ops.wgrad_lane()
     if lane is not None and lane.accepts(w):
-        lane.submit(w, g, x, upsample_in, bias=bias)
+        lane.submit(w, g, x, upsample_in, bias=bias, scale=scale)
         return None
     assert bias is None
     if upsample_in:
-        return ops.conv3x3_wgrad(g, x, upsample_in=True)
-    return ConvWgrad.apply(g, x)
+        gw = ops.conv3x3_wgrad(g, x, upsample_in=True)
+    else:
+        gw = ConvWgrad.apply(g, x)
+    return gw if scale is None else gw * scale
+
+
+def _scaled(w, scale):
+    """The weight a layer runs with: w, or w * scale for the output-scaled layers of the critic's fade-in (progan.py)."""
+    w = w.float()
+    return (w if scale is None else w * scale).contiguous()
 
 
 # The gradient penalty's double backward reaches the FORWARD graph of the critic only through the saved activations of
@@ -87,41 +95,41 @@ def _nones(ctx):
 
 
 class ConvFprop(Function):
-    """y = conv3x3(x, w), no bias / activation (linear in x and in w)."""
+    """y = conv3x3(x, w [* scale]), no bias / activation (linear in x and in w)."""
 
     @staticmethod
-    def forward(ctx, x, w):
+    def forward(ctx, x, w, scale=None):
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(x, w)
-        return ops.conv3x3(_act(x), w.float().contiguous())
+        ctx.save_for_backward(x, w, scale)
+        return ops.conv3x3(_act(x), _scaled(w, scale))
 
     @staticmethod
     def backward(ctx, gy):
         if gy is None:
             return _nones(ctx)
-        x, w = ctx.saved_tensors
-        gx = ConvDgrad.apply(gy, w) if ctx.needs_input_grad[0] else None
-        gw = _wgrad(w, gy, x) if ctx.needs_input_grad[1] and _param_grads[0] else None
-        return gx, gw
+        x, w, scale = ctx.saved_tensors
+        gx = ConvDgrad.apply(gy, w, scale) if ctx.needs_input_grad[0] else None
+        gw = _wgrad(w, gy, x, scale=scale) if ctx.needs_input_grad[1] and _param_grads[0] else None
+        return gx, gw, None
 
 
 class ConvDgrad(Function):
-    """dx = data gradient of conv3x3(., w) for output gradient g."""
+    """dx = data gradient of conv3x3(., w [* scale]) for output gradient g."""
 
     @staticmethod
-    def forward(ctx, g, w):
+    def forward(ctx, g, w, scale=None):
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(g, w)
-        return ops.conv3x3(_act(g), w.float().contiguous(), dgrad=True)
+        ctx.save_for_backward(g, w, scale)
+        return ops.conv3x3(_act(g), _scaled(w, scale), dgrad=True)
 
     @staticmethod
     def backward(ctx, gdx):
         if gdx is None:
             return _nones(ctx)
-        g, w = ctx.saved_tensors
-        gg = ConvFprop.apply(gdx, w) if ctx.needs_input_grad[0] else None
-        gw = _wgrad(w, g, gdx) if ctx.needs_input_grad[1] and _param_grads[0] else None
-        return gg, gw
+        g, w, scale = ctx.saved_tensors
+        gg = ConvFprop.apply(gdx, w, scale) if ctx.needs_input_grad[0] else None
+        gw = _wgrad(w, g, gdx, scale=scale) if ctx.needs_input_grad[1] and _param_grads[0] else None
+        return gg, gw, None
 
 
 class ConvWgrad(Function):
@@ -152,32 +160,37 @@ def _lrelu_mask(y: th.Tensor) -> th.Tensor:
 class ConvBiasLReLU(Function):
     """y = LeakyReLU_0.2(conv3x3(x, w) + b), bias and activation fused in the kernel epilogue.
     Backward is composed of differentiable pieces (mask multiply, ConvDgrad, ConvWgrad), so double backward works.
-    Reference: discriminator.py:15-22,26-33 (Conv2d + LeakyReLU pairs of ConvBlock)."""
+    Reference: discriminator.py:15-22,26-33 (Conv2d + LeakyReLU pairs of ConvBlock).
+    `scale` (0-dim tensor >= 0, no gradient): the layer runs with w * scale and b * scale, i.e. y = scale * LeakyReLU(conv(x, w)
+    + b) -- LeakyReLU is positively homogeneous -- which is how the critic's fade-in weights its two paths without a pass
+    over the blended activations (progan.Discriminator.forward)."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, scale=None):
         ctx.set_materialize_grads(False)
-        y = ops.conv3x3(_act(x), w.float().contiguous(), b.float().contiguous(), lrelu=True, split_w=True, exact_w=True)
-        ctx.save_for_backward(x, w, y, b)
+        y = ops.conv3x3(_act(x), _scaled(w, scale), _scaled(b, scale), lrelu=True, split_w=True, exact_w=True)
+        ctx.save_for_backward(x, w, y, b, scale)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         if gy is None:
             return _nones(ctx)
-        x, w, y, b = ctx.saved_tensors
+        x, w, y, b, scale = ctx.saved_tensors
         want_gw = ctx.needs_input_grad[1] and _param_grads[0]
         want_gb = ctx.needs_input_grad[2] and _param_grads[0]
-        lane_b = want_gw and want_gb and _lane_bias(w, b, y)
+        lane_b = want_gw and want_gb and scale is None and _lane_bias(w, b, y)
         if _UNFUSED_LRELU_BWD:
             gz = gy * _lrelu_mask(y)
             gb = gz.float().sum(dim=(0, 2, 3))
             lane_b = False
         else:
             gz, gb = LReLUBwd.apply(gy, y, want_gb and not lane_b)
-        gx = ConvDgrad.apply(gz, w) if ctx.needs_input_grad[0] else None
-        gw = _wgrad(w, gz, x, bias=b if lane_b else None) if want_gw else None
-        return gx, gw, (gb if ctx.needs_input_grad[2] and not lane_b else None)
+        if gb is not None and scale is not None:
+            gb = gb * scale
+        gx = ConvDgrad.apply(gz, w, scale) if ctx.needs_input_grad[0] else None
+        gw = _wgrad(w, gz, x, bias=b if lane_b else None, scale=scale) if want_gw else None
+        return gx, gw, (gb if ctx.needs_input_grad[2] and not lane_b else None), None
 
 
 class LReLUBwd(Function):

@@ -402,13 +402,21 @@ class WgradLane:
             self.out[i] = th.empty(tuple(p.shape), dtype=th.float32, device=p.device)
         return self.out[i], first
 
-    def submit(self, w: th.Tensor, g: th.Tensor, x: th.Tensor, upsample_in: bool = False, bias=None) -> None:
+    def submit(self, w: th.Tensor, g: th.Tensor, x: th.Tensor, upsample_in: bool = False, bias=None, scale=None) -> None:
         cur = self.origin
         dw, first = self._slot(w)
         db, first_b = self._slot(bias) if bias is not None else (None, True)
         self.stream.wait_stream(cur)
         with th.cuda.stream(self.stream):
-            conv3x3_wgrad(g, x, upsample_in=upsample_in, out=dw, accumulate=not first, bias_out=db, accumulate_bias=not first_b)
+            if scale is None:
+                conv3x3_wgrad(g, x, upsample_in=upsample_in, out=dw, accumulate=not first, bias_out=db, accumulate_bias=not first_b)
+            else:                  # the layer ran with w * scale: its contribution is scale * wgrad (two tiny kernels)
+                assert bias is None
+                tmp = conv3x3_wgrad(g, x, upsample_in=upsample_in)
+                if first:
+                    th.mul(tmp, scale, out=dw)
+                else:
+                    dw.addcmul_(tmp, scale)
             ev = th.cuda.Event()
             ev.record(self.stream)
         # g and x were allocated on the origin stream: they stay referenced until that stream has waited for the lane
