@@ -307,9 +307,11 @@ struct SplitPlan { int Nt, n_slices, stages, tmem_cols; unsigned stage_bytes; si
 
 static SplitPlan plan_split(int Cin, int Cout, bool full_n, int n_tiles, int wparts) {
     SplitPlan pl{};
-    // layers with several waves of tiles run TWO CTAs per SM (each gets half of the shared memory, i.e. a shorter ring):
-    // load, MMA and epilogue phases of neighbouring tiles then overlap; small layers keep one CTA with a deep ring
-    const int two_cta_tiles = getenv("MG_SPLIT_2CTA_TILES") ? atoi(getenv("MG_SPLIT_2CTA_TILES")) : 0;
+    // layers with at least 128 tiles run TWO CTAs per SM (each gets half of the shared memory, i.e. a shorter ring and
+    // narrower slices): the kernel is not persistent, so the prologue / load / MMA / epilogue phases of neighbouring tiles
+    // only overlap across CTAs (scripts/sweep_split.py: 64 x 64 layers at batch 16 -20 %, 32 x 32 at batch 16 -18 %; layers
+    // with 64 tiles or fewer lose 20 % and keep one CTA with a deep ring).  MG_SPLIT_2CTA_TILES overrides (0 = never).
+    const int two_cta_tiles = getenv("MG_SPLIT_2CTA_TILES") ? atoi(getenv("MG_SPLIT_2CTA_TILES")) : 128;
     const size_t budget = (!full_n && two_cta_tiles > 0 && n_tiles >= two_cta_tiles ? 108 : 216) * 1024;
     // slice width.  An M128 x N x K16 MMA from shared memory costs max(32, N / 2) cycles (the A tile is re-read by every
     // MMA), so N <= 64 is as fast per CTA as it gets: layers with fewer tiles than SMs (latency bound) use narrow slices
