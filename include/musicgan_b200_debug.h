@@ -29,6 +29,10 @@ int mg_debug_mma_pace(long long* cycles_dev, int N, int n_mma, int n_acc, int mo
  * an SM); cycles_dev[cta] = that CTA's ticks. */
 int mg_debug_mma_pace_grid(long long* cycles_dev, int N, int n_mma, int ctas, mgStream stream);
 
+/* Contention probe: a chain of n_mma MMAs (N columns) while four warps drain `ld_cols` other accumulator columns in a loop.
+ * out_dev[0] = ticks of the chain, out_dev[1] = 16-column loads completed by each draining warp meanwhile. */
+int mg_debug_mma_vs_drain(long long* out_dev, int N, int n_mma, int ld_cols, mgStream stream);
+
 #ifdef __cplusplus
 }
 #endif

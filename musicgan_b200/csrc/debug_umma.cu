@@ -289,3 +289,67 @@ extern "C" int mg_debug_mma_pace(long long* cycles, int N, int n_mma, int n_acc,
     k_debug_mma_pace<<<1, 128, 49 * 1024, (cudaStream_t)stream>>>(cycles, N, n_mma, n_acc, mode, 512);
     return check_launch("k_debug_mma_pace");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Do accumulator drains (tcgen05.ld) and MMAs contend?  Warp 1 issues a chain of n_mma M128 x N x K16 MMAs into columns
+// [0, N); warps 4..7 (one per TMEM lane quarter) meanwhile read `ld_cols` OTHER columns in a loop (32x32b.x16 loads) until
+// the chain has completed.  out[0] = ticks of the chain, out[1] = number of 16-column loads each loader warp completed.
+// ------------------------------------------------------------------------------------------------
+namespace mg {
+__global__ void __launch_bounds__(256)
+k_debug_mma_vs_drain(long long* __restrict__ out, int N, int n_mma, int ld_cols) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    __shared__ volatile int done;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 48 * 1024 / 16; i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == 0) tmem_alloc(&tmem_base, 512);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); done = 0; }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = tmem_base;
+    if (warp == 1) {
+        const uint32_t idesc = instr_desc_bf16(N, false, false);
+        const uint32_t a0 = (smem_u32(smem) + 127u) & ~127u, b0 = a0 + 24 * 1024;
+        const uint64_t da0 = smem_desc(a0, 3072u, 160u);
+        const uint64_t db0 = smem_desc(b0, (uint32_t)N * 16u, 128u);
+        const long long t0 = clock64();
+        if (elect_one()) {
+            for (int i = 0; i < n_mma; ++i) mma_bf16(tm, da0, db0, idesc, 1u);
+            mma_commit(&bar);
+        }
+        __syncwarp();
+        mbar_wait(&bar, 0);
+        if (lane == 0) { out[0] = clock64() - t0; done = 1; }
+    } else if (warp >= 4 && ld_cols > 0) {
+        const uint32_t taddr = tm + 256 + ((uint32_t)((warp & 3) * 32) << 16);
+        long long n = 0;
+        float sink = 0.0f;
+        while (!done) {
+            for (int c = 0; c < ld_cols; c += 16) {
+                float v[16];
+                tmem_ld16(taddr + c, v);
+                tmem_wait_ld();
+                sink += v[0];
+                ++n;
+            }
+        }
+        if (lane == 0 && warp == 4) out[1] = n;
+        if (sink == 123.456f) out[2] = 1;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 512);
+}
+}  // namespace mg
+
+extern "C" int mg_debug_mma_vs_drain(long long* out, int N, int n_mma, int ld_cols, mgStream stream) {
+    using namespace mg;
+    if (!out || N % 16 || N < 16 || N > 256 || ld_cols < 0 || ld_cols > 256 || (ld_cols & 15) || n_mma < 1) return MG_ERR_BAD_ARG;
+    cudaFuncSetAttribute(k_debug_mma_vs_drain, cudaFuncAttributeMaxDynamicSharedMemorySize, 49 * 1024);
+    k_debug_mma_vs_drain<<<1, 256, 49 * 1024, (cudaStream_t)stream>>>(out, N, n_mma, ld_cols);
+    return check_launch("k_debug_mma_vs_drain");
+}

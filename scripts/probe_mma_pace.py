@@ -43,3 +43,16 @@ for N in (32, 64):
             th.cuda.synchronize()
         med = buf.double().median().item() / 512
         print(f"N {N:3d}  {per_sm} CTA/SM: per-CTA {med:6.1f}  -> per SM {med / per_sm:6.1f}   (max {buf.max().item() / 512:6.1f})")
+
+print("MMA chain while four warps drain other accumulator columns (tcgen05.ld 32x32b.x16 in a loop):")
+l.mg_debug_mma_vs_drain.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p]
+buf = th.zeros(4, dtype=th.int64, device="cuda")
+for N in (32, 64, 128):
+    for ld_cols in (0, 64, 128):
+        for _ in range(2):
+            buf.zero_()
+            assert l.mg_debug_mma_vs_drain(buf.data_ptr(), N, 1024, ld_cols, None) == 0
+            th.cuda.synchronize()
+        t, n = buf[0].item(), buf[1].item()
+        rate = n * 4 * 32 * 16 * 4 / t if t else 0.0
+        print(f"N {N:3d} drain {ld_cols:3d} cols: {t / 1024:6.1f} cycles per MMA, drained {rate:6.1f} B/clk")
