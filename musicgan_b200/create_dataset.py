@@ -25,11 +25,7 @@ def _wav_sample_count(path: str) -> int:
 
 def create_dataset(audio_path: str, dataset_output_dir: str, *, packed: bool = False) -> None:
     w_p = glob.glob(audio_path)
-    try:                      # every rank of a torchrun launch gets here: creating must not race with testing
-        mkdir(dataset_output_dir)
-    except FileExistsError:
-        if not isdir(dataset_output_dir):
-            raise NotADirectoryError(f"\"{dataset_output_dir}\" is not a directory") from None
+    parallel.ensure_dir(dataset_output_dir, f"\"{dataset_output_dir}\" is not a directory")      # every rank of a torchrun launch gets here
 
     nb_vec = audio.N_VEC
     rank, ws = parallel.world()

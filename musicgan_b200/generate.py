@@ -13,11 +13,7 @@ from .networks import Generator
 
 def generate(output_dir: str, rand_channels: int, gen_dict_state: str, nb_vec: int, nb_music: int,
              sub_batch: int = 4) -> None:
-    try:                      # every rank of a torchrun launch gets here: creating must not race with testing
-        mkdir(output_dir)
-    except FileExistsError:
-        if not isdir(output_dir):
-            raise NotADirectoryError(f"\"{output_dir}\" is not a directory") from None
+    parallel.ensure_dir(output_dir, f"\"{output_dir}\" is not a directory")      # every rank of a torchrun launch gets here
 
     print("Load model...")
     gen = Generator(rand_channels, end_layer=7)

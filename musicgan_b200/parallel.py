@@ -107,3 +107,15 @@ def _all_reduce_mean(flat: th.Tensor, ws: int) -> None:
     else:                                                   # gloo (CPU tests) has no AVG
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         flat.mul_(1.0 / ws)
+
+
+def ensure_dir(path: str, not_a_directory_message: str) -> None:
+    """Create `path` like the reference's entry points do (one `mkdir`, the parent must exist; a non-directory in the way
+    raises NotADirectoryError with the reference's message) -- but safely when EVERY rank of a torchrun launch calls it:
+    the reference's test-then-create (create_dataset.py:27-31, generate.py:25-29, train.py:48-52) races between ranks."""
+    import os
+    try:
+        os.mkdir(path)
+    except FileExistsError:
+        if not os.path.isdir(path):
+            raise NotADirectoryError(not_a_directory_message) from None

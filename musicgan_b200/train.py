@@ -36,11 +36,7 @@ def train(run_name: str, input_dataset_path: str, output_dir: str, *,
           fadein_lengths=(1, 25000, 37500, 50000, 62500, 75000, 87500, 100000)) -> None:
     assert isdir(input_dataset_path), \
         f"\"{input_dataset_path}\" doesn't exist or is not a directory"
-    try:                      # every rank of a torchrun launch gets here: creating must not race with testing
-        mkdir(output_dir)
-    except FileExistsError:
-        if not isdir(output_dir):
-            raise NotADirectoryError(f"\"{output_dir}\" is not a directory !") from None
+    parallel.ensure_dir(output_dir, f"\"{output_dir}\" is not a directory !")      # every rank of a torchrun launch gets here
 
     rank, ws = parallel.world()
     if seed is not None:

@@ -106,3 +106,37 @@ def test_real_batch_transform_matches_torch_antialias_resize(size):
         ref = F.interpolate(ref, size=(size, size), mode="bilinear", antialias=True, align_corners=False)
     got = g.scale_transform(x)
     torch.testing.assert_close(got, ref, rtol=1e-5, atol=2e-6)
+
+
+def _mk(path, q):
+    from musicgan_b200 import parallel
+    try:
+        parallel.ensure_dir(path, "not a directory")
+        q.put("ok")
+    except Exception as e:      # noqa: BLE001
+        q.put(type(e).__name__)
+
+
+def test_ensure_dir_is_safe_between_ranks(tmp_path):
+    """Every rank of a torchrun launch creates the output directory of create_dataset / train / generate: the reference's
+    exists()-then-mkdir() raises FileExistsError in the loser (seen on two GPUs); ensure_dir must not, and must keep the
+    reference's errors (a file in the way, a missing parent)."""
+    import multiprocessing as mp
+    from musicgan_b200 import parallel
+    ctx = mp.get_context("spawn")
+    for rep in range(3):
+        target = str(tmp_path / f"out{rep}")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_mk, args=(target, q)) for _ in range(6)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join()
+        assert sorted(q.get() for _ in procs) == ["ok"] * 6
+        assert os.path.isdir(target)
+    f = tmp_path / "a_file"
+    f.write_text("x")
+    with pytest.raises(NotADirectoryError):
+        parallel.ensure_dir(str(f), "not a directory")
+    with pytest.raises(FileNotFoundError):
+        parallel.ensure_dir(str(tmp_path / "missing" / "child"), "not a directory")
