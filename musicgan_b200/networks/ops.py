@@ -26,6 +26,11 @@ SPLIT_W = os.environ.get("MG_SPLIT_W", "1") != "0"
 # ... up to this output height.  Measured on B200: leaving the 512 x 512 layers on plain bf16 weights (256) buys 1 % of step
 # time and moves the stage-7 batch-1 generator-step gradient from 7.8e-3 to 9.1e-3 of the oracle's: not taken.
 SPLIT_W_MAX_RES = int(os.environ.get("MG_SPLIT_W_MAX_RES", "512"))
+# The critic's forward convolutions on the precise path take the fp32 weight exactly (three bf16 parts) up to this output
+# height: it is the 1 x 1 ... 32 x 32 layers where a single pre-activation within 1e-5 of zero moves the penalty gradient by
+# percents (golden case stage2_b3); at 64 x 64 two parts give the same errors to three digits (scripts/precision_study.py
+# emulation, stages 4-7: G-step 7.6e-4 / 4.4e-3 / 8.0e-3 / 6.3e-3 either way) and the layer runs 10-40 % faster.
+EXACT_W_MAX_RES = int(os.environ.get("MG_EXACT_W_MAX_RES", "32"))
 
 
 # Inference (module in eval mode, autograd off: `generate`) has no gradients whose masks need protecting: the forward-only
@@ -290,7 +295,7 @@ def conv3x3(x: th.Tensor, w: th.Tensor, bias=None, *, lrelu=False, pixelnorm=Fal
         assert bias.dtype == th.float32 and bias.numel() == cout and bias.is_cuda
     _account(2.0 * B * H * W * 9 * cin * cout, float(x.element_size()) * (x.numel() + y.numel()))
     if precise:
-        if exact_w and not pixelnorm:
+        if exact_w and not pixelnorm and H <= EXACT_W_MAX_RES:
             flags |= FLAG_W3
         kind = ("split", (1 if dgrad else 0) | (2 if flags & FLAG_W3 else 0))
         packed = _packed_weights(w, cin, cout, kind)
